@@ -1,0 +1,139 @@
+// Internal declarations shared by the translation units of libldpc_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "ldpc_b200.h"
+
+namespace ldpcb {
+
+constexpr int N = LDPCB_N;      // 128 code bits
+constexpr int M = LDPCB_M;      // 64 checks
+constexpr int K = LDPCB_K;      // 64 information bits
+constexpr int DC = LDPCB_MAX_CHK_DEG;  // 8
+constexpr int DV = LDPCB_MAX_VAR_DEG;  // 8
+constexpr int NUM_WS = 4;       // workspace slots (0: device pipeline, 1..3: host pipeline streams)
+
+// ---- NMS tables (device, built once per handle; reference: the dense H of ms_test.py:126,182) ----
+// Shared-memory layout of one frame in the NMS kernel, in floats:
+//   T[0..127]   per-variable total (sum of incoming cv + w_vc*y), T[128] = +inf (padding edges)
+//   CV[e*64+c]  check->variable message of edge e (0..7) of check c, at float offset NMS_CV_OFF
+//   CV[512] = 0 (padding for variables of low degree), CV[513] = dump slot for padded check edges
+constexpr int NMS_T_FLOATS = 132;
+constexpr int NMS_CV_OFF = NMS_T_FLOATS;
+constexpr int NMS_CV_FLOATS = 516;
+constexpr int NMS_FRAME_FLOATS = NMS_T_FLOATS + NMS_CV_FLOATS;  // 648 floats = 2592 B
+
+struct NmsTables {
+    // chk_var[c][e]: variable index of edge e of check c (ascending), 128 = padding
+    uint8_t chk_var[M][DC];
+    // var_slot[v][d]: CV index (e*64+c) of the d-th incoming edge of variable v, checks ascending
+    // (the summation order of tf.reduce_sum(cv_matrix, 1) restated in oracle/nms_oracle.py); 512 = padding
+    uint16_t var_slot[N][DV];
+    // chk_mask[c][w]: bit-packed row c of H (syndrome)
+    uint32_t chk_mask[M][4];
+    int max_var_deg_lo;  // max variable degree over columns 0..63
+    int max_var_deg_hi;  // max variable degree over columns 64..127
+};
+
+// ---- OSD ----
+constexpr int OSD_LUT_BYTES = 8 * 256 * 8;
+struct TepTable {
+    uint32_t* dev = nullptr;      // packed TEPs
+    std::vector<uint32_t> host;
+    int n = 0;
+    int maxw = 0;
+};
+
+struct Workspace {
+    char* buf = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace ldpcb
+
+struct ldpcb_handle {
+    int device = 0;
+    int sm_count = 0;
+    std::string err;
+    uint8_t H[ldpcb::M * ldpcb::N];
+    uint8_t G[ldpcb::K * ldpcb::N];
+    ldpcb::NmsTables nms_host;
+    ldpcb::NmsTables* nms_dev = nullptr;
+    uint64_t* gcol_dev = nullptr;  // [128] column j of G, bit r = G[r][j]
+    uint64_t gcol_host[ldpcb::N];
+    ldpcb::TepTable tep[4][2];      // [order][tep_order]
+    int32_t* one_block_dev = nullptr;  // {0, n} scratch for single-block calls
+    ldpcb::Workspace ws[ldpcb::NUM_WS];
+    cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t events[3] = {nullptr, nullptr, nullptr};
+    uint64_t launches = 0;
+};
+
+namespace ldpcb {
+
+int set_error(ldpcb_handle* h, int code, const char* fmt, ...);
+int check_cuda(ldpcb_handle* h, cudaError_t e, const char* what);
+// Grow workspace slot `slot` to at least `bytes` (cudaMalloc on growth only).
+int ensure_ws(ldpcb_handle* h, int slot, size_t bytes);
+
+#define LDPCB_CUDA(h, call)                                         \
+    do {                                                            \
+        int _st = ldpcb::check_cuda((h), (call), #call);            \
+        if (_st != LDPCB_OK) return _st;                            \
+    } while (0)
+
+#define LDPCB_LAUNCH_CHECK(h, name)                                 \
+    do {                                                            \
+        (h)->launches++;                                            \
+        int _st = ldpcb::check_cuda((h), cudaGetLastError(), name); \
+        if (_st != LDPCB_OK) return _st;                            \
+    } while (0)
+
+// kernels' host launchers (device pointers, asynchronous)
+struct NmsArgs {
+    const float* llr;
+    const int32_t* idx;  // optional frame indirection (NULL = identity)
+    int64_t B;
+    int iters;
+    float alpha, w_vc, w_marg;
+    int early_stop;
+    uint32_t* hard_bits;
+    uint8_t* iters_used;
+    uint8_t* syndrome_nz;
+    float* soft_traj;
+};
+int launch_nms(ldpcb_handle* h, const NmsArgs& a, cudaStream_t st);
+
+struct OsdArgs {
+    const float* order_llr;
+    const float* score_llr;
+    const int32_t* idx;    // optional: frame i reads/writes row idx[i]
+    const int32_t* count;  // optional device count (number of frames), else B
+    int64_t B;             // upper bound on frames (grid sizing)
+    const uint32_t* teps;
+    int n_teps;
+    int maxw;
+    const int32_t* block_start;  // NULL => one block [0,n_teps)
+    int n_blocks;
+    int flags;
+    uint32_t* cw_bits;
+    int32_t* best_tep;
+    int64_t* best_score_q;
+    int32_t* score_exp;
+    uint8_t* perm;
+    uint64_t* redG;
+    int64_t* block_min_q;
+    int32_t* block_arg;
+    const uint32_t* truth_bits;
+    int64_t* truth_score_q;
+};
+int launch_osd(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st);
+
+int build_tep_tables(ldpcb_handle* h);
+
+}  // namespace ldpcb

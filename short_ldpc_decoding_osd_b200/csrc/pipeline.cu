@@ -1,0 +1,305 @@
+// The whole hot path as one stream-ordered sequence of launches, and the host-buffer entry points.
+//
+// Device pipeline (no host synchronisation anywhere):
+//   NMS on all frames -> stable compaction of the frames with a non-zero syndrome -> OSD on those
+//   frames' channel LLRs (row 0 of the reference's 13-row retest record, PB_OSD/pb_testing.py:71-72),
+//   the OSD kernel reads the failure count from device memory -> decisions merged in place -> tallies.
+// This is the Ldpc_128_testing -> ldpc-nonzero-retest.tfrecord -> PB_OSD/FS_OSD chain of the reference
+// ("Training and Testing recipe.txt":14-18) without the files in between.
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+#include "internal.cuh"
+
+namespace ldpcb {
+
+struct Carver {
+    char* base;
+    size_t off = 0;
+    explicit Carver(char* b) : base(b) {}
+    template <typename T>
+    T* take(size_t n) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+struct DecodeWs {
+    uint8_t* syn;
+    uint8_t* iters;
+    int32_t* idx;
+    int32_t* count;
+    void* sel_temp;
+    size_t bytes;
+};
+
+static DecodeWs carve_decode(char* base, size_t start, int64_t B) {
+    Carver c(base);
+    c.off = start;
+    DecodeWs w;
+    w.syn = c.take<uint8_t>((size_t)B);
+    w.iters = c.take<uint8_t>((size_t)B);
+    w.idx = c.take<int32_t>((size_t)B);
+    w.count = c.take<int32_t>(1);
+    w.sel_temp = c.take<char>(select_temp_bytes(B));
+    w.bytes = c.off + 256;
+    return w;
+}
+
+struct DecodeParams {
+    int iters;
+    float alpha, w_vc, w_marg;
+    int early_stop, osd_order, tep_order;
+};
+
+// llr/final_bits/... are device pointers; `w` is workspace carved by the caller for this call.
+static int decode_on_device(ldpcb_handle* h, const DecodeWs& w, const float* llr, int64_t B, const DecodeParams& p,
+                            uint32_t* final_bits, uint8_t* syn_out, int32_t* best_tep, const uint32_t* truth,
+                            uint64_t* counters, cudaStream_t st) {
+    uint8_t* syn = syn_out ? syn_out : w.syn;
+    NmsArgs n;
+    n.llr = llr; n.idx = nullptr; n.B = B; n.iters = p.iters;
+    n.alpha = p.alpha; n.w_vc = p.w_vc; n.w_marg = p.w_marg; n.early_stop = p.early_stop;
+    n.hard_bits = final_bits; n.iters_used = w.iters; n.syndrome_nz = syn; n.soft_traj = nullptr;
+    int s = launch_nms(h, n, st);
+    if (s != LDPCB_OK) return s;
+    if (truth && counters) {
+        s = launch_tally_nms(h, final_bits, syn, w.iters, truth, B, counters, st);
+        if (s != LDPCB_OK) return s;
+    }
+    if (best_tep) LDPCB_CUDA(h, cudaMemsetAsync(best_tep, 0xFF, sizeof(int32_t) * (size_t)B, st));
+    if (p.osd_order >= 0) {
+        s = launch_select(h, syn, B, w.idx, w.count, w.sel_temp, st);
+        if (s != LDPCB_OK) return s;
+        const TepTable& t = h->tep[p.osd_order][p.tep_order];
+        OsdArgs a = {};
+        a.order_llr = llr; a.score_llr = llr; a.idx = w.idx; a.count = w.count; a.B = B;
+        a.teps = t.dev; a.n_teps = t.n; a.maxw = t.maxw; a.flags = 0;
+        a.cw_bits = final_bits; a.best_tep = best_tep;
+        s = launch_osd(h, a, st);
+        if (s != LDPCB_OK) return s;
+    }
+    if (truth && counters) {
+        s = launch_tally_final(h, final_bits, p.osd_order >= 0 ? syn : nullptr, best_tep, p.osd_order, p.tep_order, truth, B, counters, st);
+        if (s != LDPCB_OK) return s;
+    }
+    return LDPCB_OK;
+}
+
+static int check_decode_params(ldpcb_handle* h, const char* fn, int64_t B, const DecodeParams& p) {
+    if (B < 0 || B > 0x7fffffff) return set_error(h, LDPCB_ERR_ARG, "%s: B=%lld out of range", fn, (long long)B);
+    if (p.iters < 0 || p.iters > LDPCB_MAX_ITERS) return set_error(h, LDPCB_ERR_ARG, "%s: iters=%d out of range", fn, p.iters);
+    if (p.osd_order < -1 || p.osd_order > 3 || p.tep_order < 0 || p.tep_order > 1)
+        return set_error(h, LDPCB_ERR_ARG, "%s: osd_order=%d tep_order=%d out of range", fn, p.osd_order, p.tep_order);
+    return LDPCB_OK;
+}
+
+}  // namespace ldpcb
+
+using namespace ldpcb;
+
+extern "C" int ldpcb_decode(ldpcb_t* h, const float* llr_dev, int64_t B, int iters, float alpha_check, float w_vc,
+                            float w_marg, int early_stop, int osd_order, int tep_order, uint32_t* final_bits_dev,
+                            uint8_t* syndrome_nz_dev, int32_t* best_tep_dev, const uint32_t* truth_bits_dev,
+                            uint64_t* counters_dev, void* stream) {
+    if (!h) return LDPCB_ERR_ARG;
+    DecodeParams p{iters, alpha_check, w_vc, w_marg, early_stop, osd_order, tep_order};
+    int s = check_decode_params(h, "ldpcb_decode", B, p);
+    if (s != LDPCB_OK) return s;
+    if (B == 0) return LDPCB_OK;
+    if (!llr_dev || !final_bits_dev) return set_error(h, LDPCB_ERR_ARG, "ldpcb_decode: NULL llr or final_bits");
+    if ((uintptr_t)llr_dev & 15) return set_error(h, LDPCB_ERR_ALIGN, "ldpcb_decode: llr must be 16-byte aligned");
+    DecodeWs probe = carve_decode(nullptr, 0, B);
+    if ((s = ensure_ws(h, 0, probe.bytes)) != LDPCB_OK) return s;
+    DecodeWs w = carve_decode(h->ws[0].buf, 0, B);
+    return decode_on_device(h, w, llr_dev, B, p, final_bits_dev, syndrome_nz_dev, best_tep_dev, truth_bits_dev,
+                            counters_dev, (cudaStream_t)stream);
+}
+
+extern "C" int ldpcb_simulate(ldpcb_t* h, uint64_t seed, uint64_t first_frame, int64_t B, float ebn0_db, int iters,
+                              float alpha_check, float w_vc, float w_marg, int early_stop, int osd_order,
+                              int tep_order, uint64_t* counters_dev, void* stream) {
+    if (!h) return LDPCB_ERR_ARG;
+    DecodeParams p{iters, alpha_check, w_vc, w_marg, early_stop, osd_order, tep_order};
+    int s = check_decode_params(h, "ldpcb_simulate", B, p);
+    if (s != LDPCB_OK) return s;
+    if (B == 0) return LDPCB_OK;
+    if (!counters_dev) return set_error(h, LDPCB_ERR_ARG, "ldpcb_simulate: NULL counters");
+    Carver c(nullptr);
+    c.take<float>((size_t)B * N);
+    c.take<uint32_t>((size_t)B * 4);
+    c.take<uint32_t>((size_t)B * 4);
+    c.take<int32_t>((size_t)B);
+    const size_t head = c.off;
+    DecodeWs probe = carve_decode(nullptr, head, B);
+    if ((s = ensure_ws(h, 0, probe.bytes)) != LDPCB_OK) return s;
+    Carver d(h->ws[0].buf);
+    float* llr = d.take<float>((size_t)B * N);
+    uint32_t* truth = d.take<uint32_t>((size_t)B * 4);
+    uint32_t* bits = d.take<uint32_t>((size_t)B * 4);
+    int32_t* best = d.take<int32_t>((size_t)B);
+    DecodeWs w = carve_decode(h->ws[0].buf, head, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((s = launch_gen(h, seed, first_frame, B, ebn0_db, llr, truth, st)) != LDPCB_OK) return s;
+    return decode_on_device(h, w, llr, B, p, bits, nullptr, best, truth, counters_dev, st);
+}
+
+// ---- host-buffer entry points ------------------------------------------------------------------------
+// Chunks of HOST_CHUNK frames round-robin over three streams, each with its own workspace slot, so
+// chunk i+1's H2D copy and chunk i-1's D2H copy overlap chunk i's kernels.
+namespace ldpcb {
+constexpr int64_t HOST_CHUNK = 1 << 16;
+
+static int sync_streams(ldpcb_handle* h) {
+    for (int i = 0; i < 3; ++i) LDPCB_CUDA(h, cudaStreamSynchronize(h->streams[i]));
+    return LDPCB_OK;
+}
+}  // namespace ldpcb
+
+extern "C" int ldpcb_nms_decode_host(ldpcb_t* h, const float* llr_host, int64_t B, int iters, float alpha_check,
+                                     float w_vc, float w_marg, int early_stop, uint32_t* hard_bits_host,
+                                     uint8_t* iters_used_host, uint8_t* syndrome_nz_host, float* soft_traj_host) {
+    if (!h) return LDPCB_ERR_ARG;
+    if (B < 0 || iters < 0 || iters > LDPCB_MAX_ITERS) return set_error(h, LDPCB_ERR_ARG, "ldpcb_nms_decode_host: B=%lld iters=%d out of range", (long long)B, iters);
+    if (B == 0) return LDPCB_OK;
+    if (!llr_host || !hard_bits_host) return set_error(h, LDPCB_ERR_ARG, "ldpcb_nms_decode_host: NULL llr or hard_bits");
+    LDPCB_CUDA(h, cudaSetDevice(h->device));
+    const int rows = iters + 1;
+    const int64_t chunk = soft_traj_host ? std::min<int64_t>(HOST_CHUNK, 1 << 14) : HOST_CHUNK;
+    int ci = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk, ++ci) {
+        const int64_t nb = std::min(chunk, B - b0);
+        const int slot = 1 + ci % 3;
+        cudaStream_t st = h->streams[ci % 3];
+        Carver probe(nullptr);
+        probe.take<float>((size_t)nb * N); probe.take<uint32_t>((size_t)nb * 4); probe.take<uint8_t>((size_t)nb);
+        probe.take<uint8_t>((size_t)nb); if (soft_traj_host) probe.take<float>((size_t)nb * rows * N);
+        int s = ensure_ws(h, slot, probe.off + 256);
+        if (s != LDPCB_OK) return s;
+        Carver c(h->ws[slot].buf);
+        float* llr = c.take<float>((size_t)nb * N);
+        uint32_t* bits = c.take<uint32_t>((size_t)nb * 4);
+        uint8_t* it = c.take<uint8_t>((size_t)nb);
+        uint8_t* syn = c.take<uint8_t>((size_t)nb);
+        float* traj = soft_traj_host ? c.take<float>((size_t)nb * rows * N) : nullptr;
+        LDPCB_CUDA(h, cudaMemcpyAsync(llr, llr_host + b0 * N, sizeof(float) * nb * N, cudaMemcpyHostToDevice, st));
+        NmsArgs a;
+        a.llr = llr; a.idx = nullptr; a.B = nb; a.iters = iters; a.alpha = alpha_check; a.w_vc = w_vc; a.w_marg = w_marg;
+        a.early_stop = early_stop; a.hard_bits = bits; a.iters_used = it; a.syndrome_nz = syn; a.soft_traj = traj;
+        if ((s = launch_nms(h, a, st)) != LDPCB_OK) return s;
+        LDPCB_CUDA(h, cudaMemcpyAsync(hard_bits_host + b0 * 4, bits, sizeof(uint32_t) * nb * 4, cudaMemcpyDeviceToHost, st));
+        if (iters_used_host) LDPCB_CUDA(h, cudaMemcpyAsync(iters_used_host + b0, it, (size_t)nb, cudaMemcpyDeviceToHost, st));
+        if (syndrome_nz_host) LDPCB_CUDA(h, cudaMemcpyAsync(syndrome_nz_host + b0, syn, (size_t)nb, cudaMemcpyDeviceToHost, st));
+        if (traj) LDPCB_CUDA(h, cudaMemcpyAsync(soft_traj_host + b0 * rows * N, traj, sizeof(float) * nb * rows * N, cudaMemcpyDeviceToHost, st));
+    }
+    return sync_streams(h);
+}
+
+extern "C" int ldpcb_osd_decode_host(ldpcb_t* h, const float* order_llr_host, const float* score_llr_host, int64_t B,
+                                     int order, int tep_order, int flags, uint32_t* cw_bits_host,
+                                     int32_t* best_tep_host, int64_t* best_score_q_host, int32_t* score_exp_host,
+                                     uint8_t* perm_host, uint64_t* redG_host) {
+    if (!h) return LDPCB_ERR_ARG;
+    if (B < 0 || order < 0 || order > 3 || tep_order < 0 || tep_order > 1 || (flags & ~3))
+        return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_decode_host: B=%lld order=%d tep_order=%d flags=%d out of range", (long long)B, order, tep_order, flags);
+    if (B == 0) return LDPCB_OK;
+    if (!order_llr_host || !score_llr_host || !cw_bits_host) return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_decode_host: NULL llr or cw_bits");
+    LDPCB_CUDA(h, cudaSetDevice(h->device));
+    const bool same = (order_llr_host == score_llr_host);
+    const TepTable& t = h->tep[order][tep_order];
+    int ci = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += HOST_CHUNK, ++ci) {
+        const int64_t nb = std::min(HOST_CHUNK, B - b0);
+        const int slot = 1 + ci % 3;
+        cudaStream_t st = h->streams[ci % 3];
+        Carver probe(nullptr);
+        probe.take<float>((size_t)nb * N); probe.take<float>((size_t)nb * N); probe.take<uint32_t>((size_t)nb * 4);
+        probe.take<int32_t>((size_t)nb); probe.take<int64_t>((size_t)nb); probe.take<int32_t>((size_t)nb);
+        probe.take<uint8_t>((size_t)nb * N); probe.take<uint64_t>((size_t)nb * K);
+        int s = ensure_ws(h, slot, probe.off + 256);
+        if (s != LDPCB_OK) return s;
+        Carver c(h->ws[slot].buf);
+        float* ol = c.take<float>((size_t)nb * N);
+        float* sl = c.take<float>((size_t)nb * N);
+        uint32_t* bits = c.take<uint32_t>((size_t)nb * 4);
+        int32_t* bt = c.take<int32_t>((size_t)nb);
+        int64_t* bq = c.take<int64_t>((size_t)nb);
+        int32_t* ex = c.take<int32_t>((size_t)nb);
+        uint8_t* pm = c.take<uint8_t>((size_t)nb * N);
+        uint64_t* rg = c.take<uint64_t>((size_t)nb * K);
+        LDPCB_CUDA(h, cudaMemcpyAsync(ol, order_llr_host + b0 * N, sizeof(float) * nb * N, cudaMemcpyHostToDevice, st));
+        if (!same) LDPCB_CUDA(h, cudaMemcpyAsync(sl, score_llr_host + b0 * N, sizeof(float) * nb * N, cudaMemcpyHostToDevice, st));
+        OsdArgs a = {};
+        a.order_llr = ol; a.score_llr = same ? ol : sl; a.B = nb; a.teps = t.dev; a.n_teps = t.n; a.maxw = t.maxw; a.flags = flags;
+        a.cw_bits = bits; a.best_tep = bt; a.best_score_q = bq; a.score_exp = ex;
+        a.perm = perm_host ? pm : nullptr; a.redG = redG_host ? rg : nullptr;
+        if ((s = launch_osd(h, a, st)) != LDPCB_OK) return s;
+        LDPCB_CUDA(h, cudaMemcpyAsync(cw_bits_host + b0 * 4, bits, sizeof(uint32_t) * nb * 4, cudaMemcpyDeviceToHost, st));
+        if (best_tep_host) LDPCB_CUDA(h, cudaMemcpyAsync(best_tep_host + b0, bt, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, st));
+        if (best_score_q_host) LDPCB_CUDA(h, cudaMemcpyAsync(best_score_q_host + b0, bq, sizeof(int64_t) * nb, cudaMemcpyDeviceToHost, st));
+        if (score_exp_host) LDPCB_CUDA(h, cudaMemcpyAsync(score_exp_host + b0, ex, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, st));
+        if (perm_host) LDPCB_CUDA(h, cudaMemcpyAsync(perm_host + b0 * N, pm, (size_t)nb * N, cudaMemcpyDeviceToHost, st));
+        if (redG_host) LDPCB_CUDA(h, cudaMemcpyAsync(redG_host + b0 * K, rg, sizeof(uint64_t) * nb * K, cudaMemcpyDeviceToHost, st));
+    }
+    return sync_streams(h);
+}
+
+extern "C" int ldpcb_decode_host(ldpcb_t* h, const float* llr_host, int64_t B, int iters, float alpha_check, float w_vc,
+                                 float w_marg, int early_stop, int osd_order, int tep_order,
+                                 uint32_t* final_bits_host, uint8_t* syndrome_nz_host, int32_t* best_tep_host,
+                                 const uint32_t* truth_bits_host, uint64_t* counters_host) {
+    if (!h) return LDPCB_ERR_ARG;
+    DecodeParams p{iters, alpha_check, w_vc, w_marg, early_stop, osd_order, tep_order};
+    int s = check_decode_params(h, "ldpcb_decode_host", B, p);
+    if (s != LDPCB_OK) return s;
+    if (B == 0) return LDPCB_OK;
+    if (!llr_host || !final_bits_host) return set_error(h, LDPCB_ERR_ARG, "ldpcb_decode_host: NULL llr or final_bits");
+    LDPCB_CUDA(h, cudaSetDevice(h->device));
+    const bool tally = truth_bits_host && counters_host;
+    // device counters live at the head of workspace slot 0
+    if ((s = ensure_ws(h, 0, 4096)) != LDPCB_OK) return s;
+    uint64_t* counters = reinterpret_cast<uint64_t*>(h->ws[0].buf);
+    if (tally) {
+        LDPCB_CUDA(h, cudaMemsetAsync(counters, 0, sizeof(uint64_t) * LDPCB_NUM_COUNTERS, h->streams[0]));
+        LDPCB_CUDA(h, cudaEventRecord(h->events[0], h->streams[0]));
+        LDPCB_CUDA(h, cudaStreamWaitEvent(h->streams[1], h->events[0], 0));
+        LDPCB_CUDA(h, cudaStreamWaitEvent(h->streams[2], h->events[0], 0));
+    }
+    int ci = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += HOST_CHUNK, ++ci) {
+        const int64_t nb = std::min(HOST_CHUNK, B - b0);
+        const int slot = 1 + ci % 3;
+        cudaStream_t st = h->streams[ci % 3];
+        Carver probe(nullptr);
+        probe.take<float>((size_t)nb * N); probe.take<uint32_t>((size_t)nb * 4); probe.take<uint32_t>((size_t)nb * 4);
+        probe.take<uint8_t>((size_t)nb); probe.take<int32_t>((size_t)nb);
+        const size_t head = probe.off;
+        DecodeWs pw = carve_decode(nullptr, head, nb);
+        if ((s = ensure_ws(h, slot, pw.bytes)) != LDPCB_OK) return s;
+        Carver c(h->ws[slot].buf);
+        float* llr = c.take<float>((size_t)nb * N);
+        uint32_t* bits = c.take<uint32_t>((size_t)nb * 4);
+        uint32_t* truth = c.take<uint32_t>((size_t)nb * 4);
+        uint8_t* syn = c.take<uint8_t>((size_t)nb);
+        int32_t* bt = c.take<int32_t>((size_t)nb);
+        DecodeWs w = carve_decode(h->ws[slot].buf, head, nb);
+        LDPCB_CUDA(h, cudaMemcpyAsync(llr, llr_host + b0 * N, sizeof(float) * nb * N, cudaMemcpyHostToDevice, st));
+        if (tally) LDPCB_CUDA(h, cudaMemcpyAsync(truth, truth_bits_host + b0 * 4, sizeof(uint32_t) * nb * 4, cudaMemcpyHostToDevice, st));
+        s = decode_on_device(h, w, llr, nb, p, bits, syn, (best_tep_host || tally) ? bt : nullptr, tally ? truth : nullptr,
+                             tally ? counters : nullptr, st);
+        if (s != LDPCB_OK) return s;
+        LDPCB_CUDA(h, cudaMemcpyAsync(final_bits_host + b0 * 4, bits, sizeof(uint32_t) * nb * 4, cudaMemcpyDeviceToHost, st));
+        if (syndrome_nz_host) LDPCB_CUDA(h, cudaMemcpyAsync(syndrome_nz_host + b0, syn, (size_t)nb, cudaMemcpyDeviceToHost, st));
+        if (best_tep_host) LDPCB_CUDA(h, cudaMemcpyAsync(best_tep_host + b0, bt, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, st));
+    }
+    if ((s = sync_streams(h)) != LDPCB_OK) return s;
+    if (tally) {
+        uint64_t tmp[LDPCB_NUM_COUNTERS];
+        LDPCB_CUDA(h, cudaMemcpy(tmp, counters, sizeof tmp, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < LDPCB_NUM_COUNTERS; ++i) counters_host[i] += tmp[i];
+    }
+    return LDPCB_OK;
+}
