@@ -250,12 +250,18 @@ def run_dl():
                 path.append(p)
     blocks = [osd.error_pattern_gen(p, ranges) for p in path]
     acc = np.insert(np.cumsum([b.shape[0] for b in blocks]), 0, 0)
-    W = rng.normal(size=(6, 6)).astype(np.float32) * 0.3
-    V = rng.normal(size=(6, 2)).astype(np.float32)
+    # window classifier with a readable rule: stop when (2nd smallest - smallest) of the window is large,
+    # more readily at deeper positions k:  logit1 - logit0 = 2*(w[1]-w[0]) - 2.5 + 0.2*k
+    W = np.eye(6, dtype=np.float32)
+    V = np.zeros((6, 2), dtype=np.float32)
+    V[0, 1], V[1, 1], V[5, 1] = -2.0, 2.0, 0.2
+    V[:, 0] = 0.0
+    bias_trick = np.float32(2.5)
 
     def fcn(x):
         h = np.asarray(x, dtype=np.float32) @ W
         o = h @ V
+        o[..., 0] += bias_trick
         e = np.exp(o - o.max(axis=-1, keepdims=True))
         return tf.constant(e / e.sum(axis=-1, keepdims=True))
 
@@ -269,23 +275,25 @@ def run_dl():
         return v
 
     osd.acquire_min = acquire
-    per = []
+    per, mins = [], []
     idx_lists, Ms = [], []
     order_H, order_in, order_orig, order_lab = osd.check_matrix_reorder(input_list, new_inputs, lab)
     with _quiet():
         upd_idx, upd_M, swap_len, swap_pos = osd.identify_mrb(np.asarray(order_H))
     lri = np.asarray(osd.mag_input_gen(new_inputs))
     for i in range(len(y)):
+        spy["mins"] = []
         with _quiet():
             s, f, w, c = osd.sliding_osd(fcn, input_list[13 * i:13 * i + 13], new_inputs[i:i + 1], lab[i:i + 1], (blocks, acc))
         per.append((s, f, w, int(c)))
+        mins.append(spy["mins"] + [np.nan] * (len(blocks) - len(spy["mins"])))
         idx_lists.append(np.asarray(upd_idx[i]))
         Ms.append(np.packbits(np.asarray(upd_M[i]).astype(np.uint8), axis=1))
     np.savez_compressed(
         os.path.join(GOLD, "dl_ref_shim.npz"), y=y, labels=lab.astype(np.uint8), traj=traj, taps=taps, new_inputs=new_inputs,
         path=np.array(path), block_sizes=np.array([b.shape[0] for b in blocks]),
         blocks=np.packbits(np.concatenate(blocks, 0).astype(np.uint8), axis=1), boundary=np.asarray(boundary), W=W, V=V,
-        per_frame=np.array(per), lri=lri, upd_idx=np.array(idx_lists), M=np.array(Ms), swap_len=np.array(swap_len))
+        per_frame=np.array(per), block_mins_fp32=np.array(mins), fcn_bias0=bias_trick, lri=lri, upd_idx=np.array(idx_lists), M=np.array(Ms), swap_len=np.array(swap_len))
 
 
 def run_gf2():

@@ -28,6 +28,26 @@ class Tensor(np.ndarray):
     def __array_wrap__(self, arr, context=None, return_scalar=False):
         return np.asarray(arr).view(Tensor)
 
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        # TF binary ops convert the non-tensor operand with the tensor's dtype as hint
+        # (x * H with H an int64 NumPy array stays float32), unlike NumPy's promotion.
+        tdt = next(i.dtype for i in inputs if isinstance(i, Tensor))
+        conv = []
+        for i in inputs:
+            if isinstance(i, Tensor):
+                conv.append(np.asarray(i))
+            else:
+                a = np.asarray(i)
+                if ufunc.nin == 2 and a.dtype != tdt and a.dtype.kind in "iufb" and tdt.kind in "iuf":
+                    a = a.astype(tdt)
+                conv.append(a)
+        if "out" in kwargs:
+            kwargs["out"] = tuple(np.asarray(o) for o in kwargs["out"])
+        out = getattr(ufunc, method)(*conv, **kwargs)
+        if isinstance(out, tuple):
+            return tuple(np.asarray(o).view(Tensor) for o in out)
+        return np.asarray(out).view(Tensor)
+
     def __bool__(self):
         a = np.asarray(self)
         if a.size == 0:
