@@ -1,0 +1,164 @@
+"""Drop-in for the reference's NMS test model (``LDPC_128/Ldpc_128_testing/ms_test.py``).
+
+Same classes, methods, argument meaning and return shapes:
+
+* ``Decoder_Layer(initial_value=-0.048)`` with the raw (pre-softplus) weights ``shared_check_weight``
+  (and ``shared_bit_weight`` / ``shared_bit_weight1`` / ``shared_bit_weight2`` for NMS-2 / NMS-3)
+  -- ms_test.py:71-97; ``layer(soft_input, labels)`` -> list of ``num_iterations + 1`` arrays
+  ``float32[B,128]`` (index 0 = input) -- ms_test.py:99-121.
+* ``Decoding_model()(inputs, labels)`` -> ``(fer, ber, undetected_count, (buffer_inputs, buffer_labels))``
+  -- ms_test.py:30-34; ``get_eval`` -- :36-54; ``collect_failed_output_selective`` -- :55-64;
+  ``postprocess_failure_cases`` -- :66-70.
+
+All arithmetic runs in libldpc_b200.so (CUDA, sm_100a) through the host-buffer C-ABI calls; NumPy only
+reshapes the results into the reference's Python structures.  Weights exported from a TF checkpoint
+are assigned to the ``shared_*`` attributes as plain floats/arrays.
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import numpy as np
+
+from . import _lib
+from . import globalmap as GL
+from .runtime import get_handle, softplus
+
+
+def _as_llr(x) -> np.ndarray:
+    a = np.ascontiguousarray(np.asarray(x), dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] != 128:
+        raise ValueError(f"expected float[B,128] soft input, got shape {a.shape}")
+    return a
+
+
+class Decoder_Layer:
+    def __init__(self, initial_value: float = -0.048):
+        self.decoder_type = GL.get_map("selected_decoder_type") or "NMS-1"
+        self.num_iterations = int(GL.get_map("num_iterations") or 12)
+        self.code = GL.get_map("code_parameters")
+        self.initials = initial_value
+        if self.decoder_type not in ("NMS-1", "NMS-2", "NMS-3"):
+            raise NotImplementedError(f"decoder type {self.decoder_type!r}: only NMS-1/2/3 are on the hot path (ms_test.py:84-92)")
+        w = lambda: np.full([1], initial_value, dtype=np.float32)  # noqa: E731
+        self.shared_check_weight = w()
+        if self.decoder_type == "NMS-2":
+            self.shared_bit_weight = w()
+        if self.decoder_type == "NMS-3":
+            self.shared_bit_weight1 = w()
+            self.shared_bit_weight2 = w()
+
+    # (alpha, w_vc, w_marg) as the kernel takes them: softplus applied here (ms_test.py:127-131,207-208,222-226)
+    def kernel_weights(self) -> Tuple[float, float, float]:
+        alpha = softplus(np.asarray(self.shared_check_weight).reshape(-1)[0])
+        w_vc = w_marg = 1.0
+        if self.decoder_type == "NMS-2":
+            w_vc = w_marg = softplus(np.asarray(self.shared_bit_weight).reshape(-1)[0])
+        if self.decoder_type == "NMS-3":
+            w_vc = softplus(np.asarray(self.shared_bit_weight1).reshape(-1)[0])
+            w_marg = softplus(np.asarray(self.shared_bit_weight2).reshape(-1)[0])
+        return alpha, w_vc, w_marg
+
+    def __call__(self, soft_input, labels=None) -> List[np.ndarray]:
+        return self.call(soft_input, labels)
+
+    def call(self, soft_input, labels=None) -> List[np.ndarray]:
+        y = _as_llr(soft_input)
+        B = y.shape[0]
+        alpha, w_vc, w_marg = self.kernel_weights()
+        h = get_handle(self.code)
+        bits = np.empty((B, 4), np.uint32)
+        traj = np.empty((B, self.num_iterations + 1, 128), np.float32)
+        h.call("ldpcb_nms_decode_host", y, B, self.num_iterations, alpha, w_vc, w_marg, 0, bits, None, None, traj)
+        return [traj[:, i, :] for i in range(self.num_iterations + 1)]
+
+
+class Decoding_model:
+    def __init__(self):
+        self.layer = Decoder_Layer()
+
+    def __call__(self, inputs, labels):
+        return self.call(inputs, labels)
+
+    def call(self, inputs, labels):
+        """One NMS pass with tallies on the GPU, then a second pass that only re-decodes the detected
+        failures to collect their 13-row trajectories (the retest record of ms_test.py:55-64)."""
+        y = _as_llr(inputs)
+        lab = np.asarray(labels)
+        B = y.shape[0]
+        L = self.layer
+        alpha, w_vc, w_marg = L.kernel_weights()
+        h = get_handle(L.code)
+        truth = _lib.pack_bits(lab)
+        bits = np.empty((B, 4), np.uint32)
+        syn = np.empty(B, np.uint8)
+        cnt = np.zeros(_lib.NUM_COUNTERS, np.uint64)
+        h.call("ldpcb_decode_host", y, B, L.num_iterations, alpha, w_vc, w_marg, 0, -1, 0, bits, syn, None, truth, cnt)
+        fer = float(cnt[1]) / B
+        ber = float(cnt[2]) / (B * lab.shape[1])
+        undetected = int(cnt[4])
+        if undetected:
+            und = np.flatnonzero((syn == 0) & (bits != truth).any(axis=1))
+            print("Undetected Elements:", und[:, None])
+        indices = np.flatnonzero(syn)[:, None].astype(np.int64)
+        self.last_hard_bits = bits
+        self.last_counters = cnt
+        buffer = self._collect(y, lab, indices)
+        return fer, ber, undetected, buffer
+
+    def _collect(self, y, lab, indices):
+        L = self.layer
+        idx = indices[:, 0]
+        buffer_inputs, buffer_labels = [], []
+        if len(idx):
+            alpha, w_vc, w_marg = L.kernel_weights()
+            h = get_handle(L.code)
+            yf = np.ascontiguousarray(y[idx])
+            traj = np.empty((len(idx), L.num_iterations + 1, 128), np.float32)
+            bits = np.empty((len(idx), 4), np.uint32)
+            h.call("ldpcb_nms_decode_host", yf, len(idx), L.num_iterations, alpha, w_vc, w_marg, 0, bits, None, None, traj)
+            for n, i in enumerate(idx):
+                for j in range(L.num_iterations + 1):
+                    buffer_inputs.append(traj[n, j])
+                    buffer_labels.append(lab[i])
+        return buffer_inputs, buffer_labels
+
+    def get_eval(self, soft_output_list, labels):
+        """(FER, BER, n_undetected, index int64[F,1]) from the last soft output (ms_test.py:36-54).
+        The hard decision, syndrome and tallies are the kernel's (a zero-iteration decode of the given
+        posterior is exactly tf.where(x>0,0,1) + syndrome)."""
+        soft = _as_llr(soft_output_list[-1])
+        lab = np.asarray(labels)
+        B = soft.shape[0]
+        h = get_handle(self.layer.code)
+        truth = _lib.pack_bits(lab)
+        bits = np.empty((B, 4), np.uint32)
+        syn = np.empty(B, np.uint8)
+        cnt = np.zeros(_lib.NUM_COUNTERS, np.uint64)
+        h.call("ldpcb_decode_host", soft, B, 0, 1.0, 1.0, 1.0, 0, -1, 0, bits, syn, None, truth, cnt)
+        if int(cnt[4]):
+            und = np.flatnonzero((syn == 0) & (bits != truth).any(axis=1))
+            print("Undetected Elements:", und[:, None])
+        index = np.flatnonzero(syn)[:, None].astype(np.int64)
+        return float(cnt[1]) / B, float(cnt[2]) / (B * lab.shape[1]), int(cnt[4]), index
+
+    def collect_failed_output_selective(self, soft_output_list, labels, index):
+        list_length = self.layer.num_iterations + 1
+        buffer_inputs, buffer_labels = [], []
+        for i in np.asarray(index).reshape(-1):
+            for j in range(list_length):
+                buffer_inputs.append(soft_output_list[j][i])
+                buffer_labels.append(labels[i])
+        return buffer_inputs, buffer_labels
+
+    def postprocess_failure_cases(self, buffer):
+        buffer_inputs = [j for i in buffer[0] for j in i]
+        buffer_labels = [j for i in buffer[1] for j in i]
+        return buffer_inputs, buffer_labels
+
+
+def calculation_loss(soft_output, labels) -> float:
+    """Sum of sigmoid cross-entropies with logits = -soft_output (ms_test.py:244-249); log-only statistic."""
+    x = -np.asarray(soft_output, dtype=np.float64)
+    z = np.asarray(labels, dtype=np.float64)
+    return float(np.sum(np.maximum(x, 0) - x * z + np.log1p(np.exp(-np.abs(x)))))
