@@ -114,6 +114,7 @@ struct OsdArgs {
     const float* score_llr;
     const int32_t* idx;    // optional: frame i reads/writes row idx[i]
     const int32_t* count;  // optional device count (number of frames), else B
+    const uint64_t* redG_in;  // optional [B,64] P' rows: frames are already permuted, skip sort + elimination
     int64_t B;             // upper bound on frames (grid sizing)
     const uint32_t* teps;
     int n_teps;

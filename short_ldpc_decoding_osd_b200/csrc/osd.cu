@@ -1,5 +1,7 @@
-// Ordered-statistics decoding, one warp per frame, everything on chip between the LLR load and the
-// 16-byte codeword store.
+// Ordered-statistics decoding.  One CTA of four warps works on four frames at a time: each warp
+// prepares one frame (sort, elimination, P' rows, exact reliabilities), then the four warps sweep the
+// TEP list of each prepared frame together through one shared 16 KB weighted-popcount table.
+// Everything stays on chip between the 512-byte LLR load and the 16-byte codeword store.
 //
 // Replaces, per frame (reference paths relative to LDPC_128/):
 //   swapped_info           PB_OSD/pb_testing.py:306-320  (reliability sort, pi1)
@@ -8,39 +10,48 @@
 //   convention_osd_main    FS_OSD/convention_osd.py:49-77 (TEP sweep, re-encode, discrepancy, argmin)
 //   osd.acquire_min        DL_OSD_Testing_serial/ordered_statistics_decoding.py:153-162 (block minima)
 //
-// Phases of one frame:
-//   1. rank sort of the 128 keys (|y| bits, index) -> pi1; ties as tf.argsort (stable)
-//   2. column-major GF(2) elimination of G[:, pi1]: lane l holds sorted columns l, l+32, l+64, l+96
-//      as 64-bit words (bit r = row r); columns are scanned most reliable first, a column with a 1
-//      in a row not yet used becomes the next pivot (greedy most-reliable basis).  The reference's
-//      rule (row swap / column swap with the first 1 of row i) selects the same basis and its
-//      outputs depend only on that basis because identify_mrb re-sorts both halves
-//      (pb_testing.py:284-300); DESIGN.md gives the argument, tests compare with the lifted reference.
-//   3. P' rows by ballot transposition of the 64 non-pivot columns
-//   4. exact integer reliabilities q = rint(|y| * 2^(54-E)), byte LUTs of the 64 LRB weights
-//   5. TEP sweep: D = d0 ^ XOR_{t in TEP} P'_t, score = base + sum delta_t + sum_b LUT_b[byte_b(D)]
+// Prepare (one warp, one frame):
+//   1. bitonic sort of the 128 keys |y| (raw bits) with the index as payload, four keys per lane.
+//      The network is not stable, so a frame that contains two equal keys (2.7e-4 of AWGN frames,
+//      every frame of a quantised input) is re-ranked by an exact rank sort with tf.argsort's tie rule.
+//   2. column-major GF(2) elimination of G[:, pi1]: lane l holds sorted columns 4l..4l+3 as 64-bit
+//      words (bit r = row r); columns are scanned most reliable first, a column with a 1 in a row not
+//      yet used becomes the next pivot (greedy most-reliable basis).  The reference's rule (row swap /
+//      column swap with the first 1 of row i) selects the same basis and its outputs depend only on
+//      that basis because identify_mrb re-sorts both halves (pb_testing.py:284-300); DESIGN.md gives
+//      the argument, tests compare with the reference's own full_gf2elim.
+//   3. P' rows: 64x64 bit transpose of the non-pivot columns (four 32x32 warp butterflies)
+//   4. exact integer reliabilities q = rint(|y| * 2^(54-E)); order-0 codeword; per-position deltas
+// Sweep (four warps, one frame at a time):
+//   5. byte LUTs of the 64 LRB weights; for TEP i: D = d0 ^ XOR_{t in TEP} P'_t,
+//      score = base + sum delta_t + sum_b LUT_b[byte_b(D)]
 //   6. lexicographic (score, index) minimum = first minimum in enumeration order (tf.argmin)
 #include "common.cuh"
 
 namespace ldpcb {
 
-constexpr int OSD_WARPS = 2;  // warps (frames in flight) per CTA
-constexpr int OSD_THREADS = OSD_WARPS * 32;
+constexpr int OSD_FPB = 4;  // frames (= warps) per CTA
+constexpr int OSD_THREADS = OSD_FPB * 32;
 
-// per-warp shared memory (bytes)
-struct __align__(16) OsdSmem {
-    unsigned long long lut[8][256];  // 16 KB: weighted-popcount tables of the LRB (aliased by `cols` earlier)
-    unsigned long long prow[68];     // P' rows by MRB position (logical), [64] = 0 for padded TEP slots
-    long long qd[68];                // signed score delta of flipping MRB position t, [64] = 0
-    unsigned long long qlrb[64];     // q of LRB positions
-    float yo[N];                     // ordering metric
-    float ys[N];                     // scoring metric
-    unsigned int key[N];             // |yo| bits
-    unsigned char pi1[N];            // sorted position -> original index
-    unsigned char perm[N];           // permuted position (MRB then LRB) -> original index
-    unsigned char pos[N];            // permuted position -> sorted position
-    unsigned char prow_of[64];       // pivot row of MRB position t
+struct __align__(16) FrameSm {
+    unsigned long long prow[66];  // P' rows by MRB position, [64] = 0 for padded TEP slots
+    long long qd[66];             // signed score delta of flipping MRB position t, [64] = 0
+    unsigned long long qlrb[64];  // q of the LRB positions          (qd..qlrb are reused as cols[128])
+    float yo[N];                  // ordering metric (original positions)
+    float ys[N];                  // scoring metric
+    unsigned long long d0;        // order-0 discrepancy on the LRB
+    long long base;               // order-0 discrepancy weight on the MRB
+    unsigned char pi1[N];         // sorted position -> original index
+    unsigned char pos[N];         // permuted position (MRB then LRB) -> sorted position
+    unsigned char prow_of[K];     // pivot row of MRB position t
     unsigned char tmp[N];
+};
+
+struct __align__(16) OsdSmem {
+    unsigned long long lut[8][256];  // 16 KB, shared by the four frames in turn
+    FrameSm fr[OSD_FPB];
+    long long red_s[OSD_FPB][OSD_FPB];  // [frame][warp] partial minima
+    int red_i[OSD_FPB][OSD_FPB];
 };
 
 __device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) {
@@ -63,6 +74,14 @@ __device__ __forceinline__ unsigned long long warp_xor_ull(unsigned long long v)
     for (int m = 16; m; m >>= 1) v ^= shfl_xor64(v, m);
     return v;
 }
+__device__ __forceinline__ void warp_argmin(long long& s, int& i) {
+#pragma unroll
+    for (int m = 16; m; m >>= 1) {
+        const long long os = (long long)shfl_xor64((unsigned long long)s, m);
+        const int oi = __shfl_xor_sync(0xffffffffu, i, m);
+        if (os < s || (os == s && oi < i)) { s = os; i = oi; }
+    }
+}
 
 // exact integer reliability: q = rint(a * 2^(54-E)); a finite >= 0, E = frexp exponent of the frame max
 __device__ __forceinline__ long long quantize(float a, int E) {
@@ -77,290 +96,369 @@ __device__ __forceinline__ float score_abs(float y) {
     return fminf(a, 3.402823466e38f);
 }
 
+// 32x32 bit-matrix transpose across the warp: in: lane i holds word x_i; out: bit j of lane i = bit i of x_j
+__device__ __forceinline__ unsigned transpose32(unsigned x, int lane) {
+    unsigned m = 0x0000ffffu;
+#pragma unroll
+    for (int j = 16; j; j >>= 1) {
+        const unsigned y = __shfl_xor_sync(0xffffffffu, x, j);
+        x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y & m) << j));
+        m ^= m << (j >> 1);
+    }
+    return x;
+}
+
+// ---- 1. sort: descending key, payload = original index; lane holds sorted positions 4*lane + k ------
+__device__ __forceinline__ void ce_lane(unsigned& ka, unsigned& ia, unsigned& kb, unsigned& ib, bool asc) {
+    const bool sw = asc ? (ka > kb) : (ka < kb);
+    if (sw) {
+        unsigned t = ka; ka = kb; kb = t;
+        t = ia; ia = ib; ib = t;
+    }
+}
+
+__device__ __forceinline__ void bitonic_sort_desc(unsigned (&key)[4], unsigned (&idx)[4], int lane) {
+#pragma unroll
+    for (int kk = 2; kk <= N; kk <<= 1) {
+#pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            if (j >= 4) {
+                const int lm = j >> 2;
+                const bool lower = (lane & lm) == 0;
+                const bool asc = (kk < N) && ((lane & (kk >> 2)) != 0);  // final merge is descending
+                const bool keep_min = (lower == asc);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned ok = __shfl_xor_sync(0xffffffffu, key[k], lm);
+                    const unsigned oi = __shfl_xor_sync(0xffffffffu, idx[k], lm);
+                    const bool take = keep_min ? (ok < key[k]) : (ok > key[k]);  // strict: ties stay put on both sides
+                    if (take) { key[k] = ok; idx[k] = oi; }
+                }
+            } else {
+                // element index i = 4*lane + k
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if ((k & j) == 0) {
+                        const int i_bit = (kk == 2) ? (k & 2) : (kk == 4 ? (lane & 1) : (lane & (kk >> 2)));
+                        const bool asc = (kk < N) && (i_bit != 0);
+                        ce_lane(key[k], idx[k], key[k | j], idx[k | j], asc);
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <int MAXW, bool BLOCKS>
 __global__ void __launch_bounds__(OSD_THREADS) osd_kernel(OsdArgs a, const uint64_t* __restrict__ gcol) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    OsdSmem& S = reinterpret_cast<OsdSmem*>(smem_raw)[warp];
-    unsigned long long* cols = &S.lut[0][0];  // [128] columns after elimination (before the LUT is built)
+    OsdSmem& S = *reinterpret_cast<OsdSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    FrameSm& F = S.fr[warp];
+    unsigned long long* cols = reinterpret_cast<unsigned long long*>(F.qd);  // [128], dead before qd/qlrb are written
 
     const int64_t nframes = a.count ? (int64_t)*a.count : a.B;
-    const int64_t gw = (int64_t)blockIdx.x * OSD_WARPS + warp;
-    const int64_t nw = (int64_t)gridDim.x * OSD_WARPS;
     const bool ties_high = (a.flags & LDPCB_OSD_TIES_HIGH_INDEX_FIRST) != 0;
     const bool disc_from_score = (a.flags & LDPCB_OSD_DISC_HARD_FROM_SCORE) != 0;
 
-    for (int64_t f = gw; f < nframes; f += nw) {
-        const int64_t row = a.idx ? (int64_t)a.idx[f] : f;
-        __syncwarp();
-        // ---- load -----------------------------------------------------------------------------
-        {
-            const float4 v = reinterpret_cast<const float4*>(a.order_llr + row * N)[lane];
-            reinterpret_cast<float4*>(S.yo)[lane] = v;
-            const float4 w = reinterpret_cast<const float4*>(a.score_llr + row * N)[lane];
-            reinterpret_cast<float4*>(S.ys)[lane] = w;
-            uint4 kb;
-            kb.x = __float_as_uint(v.x) & 0x7fffffffu;
-            kb.y = __float_as_uint(v.y) & 0x7fffffffu;
-            kb.z = __float_as_uint(v.z) & 0x7fffffffu;
-            kb.w = __float_as_uint(v.w) & 0x7fffffffu;
-            reinterpret_cast<uint4*>(S.key)[lane] = kb;
-            if (lane == 0) { S.prow[64] = 0ull; S.qd[64] = 0ll; }
-        }
-        __syncwarp();
-        // ---- 1. rank sort, descending |y|, stable (ties: lower index first unless ties_high) ----
-        {
-            unsigned mykey[4];
-            int rank[4] = {0, 0, 0, 0};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) mykey[k] = S.key[lane + 32 * k];
-            for (int i4 = 0; i4 < N / 4; ++i4) {
-                const uint4 kk = reinterpret_cast<const uint4*>(S.key)[i4];
-                const unsigned ki[4] = {kk.x, kk.y, kk.z, kk.w};
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = 4 * i4 + u;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int j = lane + 32 * k;
-                        const bool first = ties_high ? (i > j) : (i < j);
-                        rank[k] += (ki[u] > mykey[k]) || (ki[u] == mykey[k] && first);
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) S.pi1[rank[k]] = (unsigned char)(lane + 32 * k);
-        }
-        __syncwarp();
-        // ---- 2. GF(2) elimination, column-major ------------------------------------------------
-        unsigned long long col[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) col[k] = gcol[S.pi1[lane + 32 * k]];
-        {
-            unsigned long long used = 0ull;
-            int npiv = 0, nlrb = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                for (int l = 0; l < 32; ++l) {
-                    const int c = 32 * k + l;
-                    if (npiv == K) {  // basis complete: everything left is LRB
-                        if (lane == 0) S.pos[K + nlrb] = (unsigned char)c;
-                        ++nlrb;
-                        continue;
-                    }
-                    const unsigned long long cc = shfl64(col[k], l);
-                    const unsigned long long cand = cc & ~used;
-                    if (cand == 0ull) {  // dependent on more reliable columns
-                        if (lane == 0) S.pos[K + nlrb] = (unsigned char)c;
-                        ++nlrb;
-                        continue;
-                    }
-                    const int p = __ffsll((long long)cand) - 1;
-                    used |= 1ull << p;
-                    if (lane == 0) { S.pos[npiv] = (unsigned char)c; S.prow_of[npiv] = (unsigned char)p; }
-                    ++npiv;
-                    const unsigned long long m = cc ^ (1ull << p);
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        if ((col[kk] >> p) & 1ull) col[kk] ^= m;
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) cols[lane + 32 * k] = col[k];
-        __syncwarp();
-        // ---- permutation pi2 o pi1 and the permuted metrics ------------------------------------
-        float yo[4], ys[4];
-        unsigned char pm[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int t = lane + 32 * k;
-            pm[k] = S.pi1[S.pos[t]];
-            yo[k] = S.yo[pm[k]];
-            ys[k] = S.ys[pm[k]];
-        }
-        // ---- 3. P' rows: transpose the 64 LRB columns by ballots --------------------------------
+    for (int64_t f0 = (int64_t)blockIdx.x * OSD_FPB; f0 < nframes; f0 += (int64_t)gridDim.x * OSD_FPB) {
+        const int64_t f = f0 + warp;
+        const bool active = f < nframes;
+        const int64_t row = active ? (a.idx ? (int64_t)a.idx[f] : f) : 0;
+        unsigned char pm[4] = {0, 0, 0, 0};
         unsigned long long myprow[2] = {0ull, 0ull};
-        {
-            const unsigned long long ca = cols[S.pos[K + lane]];
-            const unsigned long long cb = cols[S.pos[K + 32 + lane]];
-            for (int t = 0; t < K; ++t) {
-                const int p = S.prow_of[t];
-                const unsigned lo = __ballot_sync(0xffffffffu, (ca >> p) & 1ull);
-                const unsigned hi = __ballot_sync(0xffffffffu, (cb >> p) & 1ull);
-                if ((t & 31) == lane) myprow[t >> 5] = ((unsigned long long)hi << 32) | lo;
-            }
-        }
-        __syncwarp();  // everyone is done reading cols (aliases lut)
-        S.prow[lane] = myprow[0];
-        S.prow[lane + 32] = myprow[1];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) S.perm[lane + 32 * k] = pm[k];
-        // ---- 4. exact reliabilities ------------------------------------------------------------
-        float as[4];
-        unsigned amax_bits = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            as[k] = score_abs(ys[k]);
-            amax_bits = max(amax_bits, __float_as_uint(as[k]));
-        }
-#pragma unroll
-        for (int m = 16; m; m >>= 1) amax_bits = max(amax_bits, __shfl_xor_sync(0xffffffffu, amax_bits, m));
+        unsigned long long hd_lrb = 0ull, ho_mrb = 0ull, d0 = 0ull;
         int E = 0;
-        frexpf(__uint_as_float(amax_bits), &E);
-        long long q[4];
+        if (active) {
+            // ---- load ---------------------------------------------------------------------------
+            const float4 v = reinterpret_cast<const float4*>(a.order_llr + row * N)[lane];
+            reinterpret_cast<float4*>(F.yo)[lane] = v;
+            reinterpret_cast<float4*>(F.ys)[lane] = reinterpret_cast<const float4*>(a.score_llr + row * N)[lane];
+            if (a.redG_in) {
+                // pre-permuted frame with its systematic generator rows (convention_osd_main's inputs)
+                myprow[0] = a.redG_in[row * K + lane];
+                myprow[1] = a.redG_in[row * K + lane + 32];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) q[k] = quantize(as[k], E);
-        // hard decisions: 1 iff !(y > 0)   (convention_osd.py:54)
-        unsigned ho[4], hd[4];
+                for (int k = 0; k < 4; ++k) pm[k] = (unsigned char)(lane + 32 * k);
+                __syncwarp();
+            } else {
+                // ---- 1. sort --------------------------------------------------------------------
+                unsigned key[4] = {__float_as_uint(v.x) & 0x7fffffffu, __float_as_uint(v.y) & 0x7fffffffu,
+                                   __float_as_uint(v.z) & 0x7fffffffu, __float_as_uint(v.w) & 0x7fffffffu};
+                unsigned idx[4] = {4u * lane, 4u * lane + 1, 4u * lane + 2, 4u * lane + 3};
+                bitonic_sort_desc(key, idx, lane);
+                const unsigned nxt = __shfl_down_sync(0xffffffffu, key[0], 1);
+                const bool tie = (key[0] == key[1]) || (key[1] == key[2]) || (key[2] == key[3]) || (lane < 31 && key[3] == nxt);
+                if (__any_sync(0xffffffffu, tie)) {
+                    // exact rank sort with the tf.argsort tie rule (stable: lower index first; reversed-ascending: higher first)
+                    __syncwarp();
+                    unsigned mykey[4];
+                    int rank[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            ho[k] = !(yo[k] > 0.0f);
-            hd[k] = disc_from_score ? (unsigned)!(ys[k] > 0.0f) : ho[k];
-        }
-        // MRB: delta of flipping position t, and the base discrepancy of the order-0 MRB part
-        long long base = 0;
+                    for (int k = 0; k < 4; ++k) mykey[k] = __float_as_uint(F.yo[4 * lane + k]) & 0x7fffffffu;
+                    for (int i = 0; i < N; ++i) {
+                        const unsigned ki = __float_as_uint(F.yo[i]) & 0x7fffffffu;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const unsigned d0m = ho[k] ^ hd[k];
-            S.qd[lane + 32 * k] = d0m ? -q[k] : q[k];
-            base += d0m ? q[k] : 0ll;
-        }
-        base = warp_sum_ll(base);
-        S.qlrb[lane] = (unsigned long long)q[2];
-        S.qlrb[lane + 32] = (unsigned long long)q[3];
-        // order-0 codeword: c0_lrb = XOR of P' rows of the MRB positions whose hard decision is 1
-        unsigned long long c0 = (ho[0] ? myprow[0] : 0ull) ^ (ho[1] ? myprow[1] : 0ull);
-        c0 = warp_xor_ull(c0);
-        const unsigned long long hd_lrb =
-            (unsigned long long)__ballot_sync(0xffffffffu, hd[2]) | ((unsigned long long)__ballot_sync(0xffffffffu, hd[3]) << 32);
-        const unsigned long long ho_mrb =
-            (unsigned long long)__ballot_sync(0xffffffffu, ho[0]) | ((unsigned long long)__ballot_sync(0xffffffffu, ho[1]) << 32);
-        const unsigned long long d0 = c0 ^ hd_lrb;
-        __syncwarp();
-        // ---- byte LUTs: lut[b][x] = sum of q_lrb[8b+i] over the set bits i of x -------------------
-        {
-#pragma unroll 1
-            for (int b = 0; b < 8; ++b) {
-                unsigned long long w[8];
+                        for (int k = 0; k < 4; ++k) {
+                            const int j = 4 * lane + k;
+                            const bool first = ties_high ? (i > j) : (i < j);
+                            rank[k] += (ki > mykey[k]) || (ki == mykey[k] && first);
+                        }
+                    }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) w[i] = S.qlrb[8 * b + i];
-                unsigned long long hsum = 0ull;
+                    for (int k = 0; k < 4; ++k) F.pi1[rank[k]] = (unsigned char)(4 * lane + k);
+                    __syncwarp();
+                    const unsigned w = reinterpret_cast<const unsigned*>(F.pi1)[lane];
 #pragma unroll
-                for (int i = 0; i < 5; ++i) hsum += ((lane >> i) & 1) ? w[3 + i] : 0ull;
-                unsigned long long e[8];
-                e[0] = hsum;
-                e[1] = hsum + w[0];
-                e[2] = hsum + w[1];
-                e[3] = e[2] + w[0];
-                e[4] = hsum + w[2];
-                e[5] = e[4] + w[0];
-                e[6] = e[4] + w[1];
-                e[7] = e[6] + w[0];
-                ulonglong2* dst = reinterpret_cast<ulonglong2*>(&S.lut[b][lane * 8]);
+                    for (int k = 0; k < 4; ++k) idx[k] = (w >> (8 * k)) & 0xffu;
+                } else {
+                    reinterpret_cast<unsigned*>(F.pi1)[lane] = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
+                }
+                // ---- 2. GF(2) elimination, column-major ----------------------------------------------
+                unsigned long long col[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dst[i] = make_ulonglong2(e[2 * i], e[2 * i + 1]);
+                for (int k = 0; k < 4; ++k) col[k] = gcol[idx[k]];
+                {
+                    unsigned long long used = 0ull;
+                    int npiv = 0, nlrb = 0;
+                    for (int l = 0; l < 32; ++l) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int c = 4 * l + k;
+                            if (npiv == K) {  // basis complete: everything left is LRB
+                                if (lane == 0) F.pos[K + nlrb] = (unsigned char)c;
+                                ++nlrb;
+                                continue;
+                            }
+                            const unsigned long long cc = shfl64(col[k], l);
+                            const unsigned long long cand = cc & ~used;
+                            if (cand == 0ull) {  // dependent on more reliable columns
+                                if (lane == 0) F.pos[K + nlrb] = (unsigned char)c;
+                                ++nlrb;
+                                continue;
+                            }
+                            const int p = __ffsll((long long)cand) - 1;
+                            used |= 1ull << p;
+                            if (lane == 0) { F.pos[npiv] = (unsigned char)c; F.prow_of[npiv] = (unsigned char)p; }
+                            ++npiv;
+                            const unsigned long long m = cc ^ (1ull << p);
+                            if (m != 0ull) {  // an untouched unit column (an information position of G) needs no row operation
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk)
+                                    if ((col[kk] >> p) & 1ull) col[kk] ^= m;
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) cols[4 * lane + k] = col[k];
+                __syncwarp();
+                // ---- permutation pi2 o pi1 -----------------------------------------------------------
+#pragma unroll
+                for (int k = 0; k < 4; ++k) pm[k] = F.pi1[F.pos[lane + 32 * k]];
+                // ---- 3. P' rows: 64x64 bit transpose of the LRB columns -------------------------------
+                const unsigned long long ca = cols[F.pos[K + lane]];
+                const unsigned long long cb = cols[F.pos[K + 32 + lane]];
+                const unsigned tA = transpose32((unsigned)ca, lane);          // rows 0..31,  LRB cols 0..31
+                const unsigned tB = transpose32((unsigned)(ca >> 32), lane);  // rows 32..63, LRB cols 0..31
+                const unsigned tC = transpose32((unsigned)cb, lane);          // rows 0..31,  LRB cols 32..63
+                const unsigned tD = transpose32((unsigned)(cb >> 32), lane);  // rows 32..63, LRB cols 32..63
+                __syncwarp();  // all reads of cols are done; reuse it for the physical rows
+                unsigned long long* rowsP = cols;  // rows in physical order, first 512 B of the free cols area
+                rowsP[lane] = ((unsigned long long)tC << 32) | tA;
+                rowsP[lane + 32] = ((unsigned long long)tD << 32) | tB;
+                __syncwarp();
+                myprow[0] = rowsP[F.prow_of[lane]];
+                myprow[1] = rowsP[F.prow_of[lane + 32]];
+                __syncwarp();  // rowsP dead before qd/qlrb are written below
             }
-        }
-        __syncwarp();
-        // ---- truth score (DL success test) -------------------------------------------------------
-        if (BLOCKS && a.truth_bits && a.truth_score_q) {
-            long long ts = 0;
+            // ---- 4. permuted metrics, exact reliabilities, order-0 codeword ----------------------------
+            float yo[4], ys[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { yo[k] = F.yo[pm[k]]; ys[k] = F.ys[pm[k]]; }
+            float as[4];
+            unsigned amax_bits = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const unsigned tb = (a.truth_bits[row * 4 + (pm[k] >> 5)] >> (pm[k] & 31)) & 1u;
-                ts += (tb ^ hd[k]) ? q[k] : 0ll;
+                as[k] = score_abs(ys[k]);
+                amax_bits = max(amax_bits, __float_as_uint(as[k]));
             }
-            ts = warp_sum_ll(ts);
-            if (lane == 0) a.truth_score_q[f] = ts;
-        }
-        // ---- 5./6. TEP sweep ---------------------------------------------------------------------
-        const int nblk = BLOCKS ? a.n_blocks : 1;
-        long long best_s = 0x7fffffffffffffffll;
-        int best_i = 0x7fffffff;
-        for (int blk = 0; blk < nblk; ++blk) {
-            const int i0 = BLOCKS ? a.block_start[blk] : 0;
-            const int i1 = BLOCKS ? a.block_start[blk + 1] : a.n_teps;
-            long long bs = 0x7fffffffffffffffll;
-            int bi = 0x7fffffff;
-            for (int i = i0 + lane; i < i1; i += 32) {
-                const unsigned w = __ldg(a.teps + i);
-                unsigned long long D = d0;
-                long long s = base;
 #pragma unroll
-                for (int j = 0; j < MAXW; ++j) {
-                    const unsigned t = min((w >> (8 * j)) & 0xffu, 64u);
-                    D ^= S.prow[t];
-                    s += S.qd[t];
+            for (int m = 16; m; m >>= 1) amax_bits = max(amax_bits, __shfl_xor_sync(0xffffffffu, amax_bits, m));
+            frexpf(__uint_as_float(amax_bits), &E);
+            long long q[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) q[k] = quantize(as[k], E);
+            unsigned ho[4], hd[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                ho[k] = !(yo[k] > 0.0f);  // hard decision: 1 iff !(y > 0)   (convention_osd.py:54)
+                hd[k] = disc_from_score ? (unsigned)!(ys[k] > 0.0f) : ho[k];
+            }
+            long long base = 0;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const unsigned d0m = ho[k] ^ hd[k];
+                F.qd[lane + 32 * k] = d0m ? -q[k] : q[k];
+                base += d0m ? q[k] : 0ll;
+            }
+            base = warp_sum_ll(base);
+            F.qlrb[lane] = (unsigned long long)q[2];
+            F.qlrb[lane + 32] = (unsigned long long)q[3];
+            F.prow[lane] = myprow[0];
+            F.prow[lane + 32] = myprow[1];
+            unsigned long long c0 = (ho[0] ? myprow[0] : 0ull) ^ (ho[1] ? myprow[1] : 0ull);
+            c0 = warp_xor_ull(c0);
+            hd_lrb = (unsigned long long)__ballot_sync(0xffffffffu, hd[2]) | ((unsigned long long)__ballot_sync(0xffffffffu, hd[3]) << 32);
+            ho_mrb = (unsigned long long)__ballot_sync(0xffffffffu, ho[0]) | ((unsigned long long)__ballot_sync(0xffffffffu, ho[1]) << 32);
+            d0 = c0 ^ hd_lrb;
+            if (lane == 0) { F.d0 = d0; F.base = base; F.prow[64] = 0ull; F.qd[64] = 0ll; }  // [64]: padded TEP slots (qd aliases cols until here)
+            if (BLOCKS && a.truth_bits && a.truth_score_q) {
+                long long ts = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned tb = (a.truth_bits[row * 4 + (pm[k] >> 5)] >> (pm[k] & 31)) & 1u;
+                    ts += (tb ^ hd[k]) ? q[k] : 0ll;
                 }
-#pragma unroll
-                for (int b = 0; b < 8; ++b) s += (long long)S.lut[b][(unsigned)(D >> (8 * b)) & 0xffu];
-                if (s < bs) { bs = s; bi = i; }
+                ts = warp_sum_ll(ts);
+                if (lane == 0) a.truth_score_q[f] = ts;
             }
-            // warp argmin, lexicographic (score, index)
+        }
+        // ---- 5./6. sweep: the four warps share one LUT and take the frames in turn ----------------------
+        const int nfr = (int)((nframes - f0) < OSD_FPB ? (nframes - f0) : OSD_FPB);
+        for (int w = 0; w < nfr; ++w) {
+            const FrameSm& G = S.fr[w];
+            __syncthreads();  // frame w prepared; previous LUT no longer read
+            {
+                // lut[b][x] = sum of q_lrb[8b+i] over the set bits i of x; thread: table b, low nibble fixed
+                const int b = tid >> 4, lo = tid & 15;
+                unsigned long long wv[8];
 #pragma unroll
-            for (int m = 16; m; m >>= 1) {
-                const long long os = (long long)shfl_xor64((unsigned long long)bs, m);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
-                if (os < bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
+                for (int i = 0; i < 8; ++i) wv[i] = G.qlrb[8 * b + i];
+                unsigned long long lsum = 0ull;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) lsum += ((lo >> i) & 1) ? wv[i] : 0ull;
+                unsigned long long e[16];
+                e[0] = lsum;
+#pragma unroll
+                for (int x = 1; x < 16; ++x) e[x] = e[x & (x - 1)] + wv[4 + (31 - __clz(x & -x))];
+#pragma unroll
+                for (int x = 0; x < 16; ++x) S.lut[b][x * 16 + lo] = e[x];
             }
-            if (BLOCKS) {
+            __syncthreads();
+            const unsigned long long gd0 = G.d0;
+            const long long gbase = G.base;
+            if (!BLOCKS) {
+                long long bs = 0x7fffffffffffffffll;
+                int bi = 0x7fffffff;
+                for (int i = tid; i < a.n_teps; i += OSD_THREADS) {
+                    const unsigned tw = __ldg(a.teps + i);
+                    unsigned long long D = gd0;
+                    long long s = gbase;
+#pragma unroll
+                    for (int j = 0; j < MAXW; ++j) {
+                        const unsigned t = min((tw >> (8 * j)) & 0xffu, 64u);
+                        D ^= G.prow[t];
+                        s += G.qd[t];
+                    }
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) s += (long long)S.lut[b][(unsigned)(D >> (8 * b)) & 0xffu];
+                    if (s < bs) { bs = s; bi = i; }
+                }
+                warp_argmin(bs, bi);
+                if (lane == 0) { S.red_s[w][warp] = bs; S.red_i[w][warp] = bi; }
+            } else {
+                // block minima: warp v takes blocks v, v+4, ... of this frame
+                const int64_t fw = f0 + w;
+                for (int blk = warp; blk < a.n_blocks; blk += OSD_FPB) {
+                    const int i0 = a.block_start[blk], i1 = a.block_start[blk + 1];
+                    long long bs = 0x7fffffffffffffffll;
+                    int bi = 0x7fffffff;
+                    for (int i = i0 + lane; i < i1; i += 32) {
+                        const unsigned tw = __ldg(a.teps + i);
+                        unsigned long long D = gd0;
+                        long long s = gbase;
+#pragma unroll
+                        for (int j = 0; j < MAXW; ++j) {
+                            const unsigned t = min((tw >> (8 * j)) & 0xffu, 64u);
+                            D ^= G.prow[t];
+                            s += G.qd[t];
+                        }
+#pragma unroll
+                        for (int b = 0; b < 8; ++b) s += (long long)S.lut[b][(unsigned)(D >> (8 * b)) & 0xffu];
+                        if (s < bs) { bs = s; bi = i; }
+                    }
+                    warp_argmin(bs, bi);
+                    if (lane == 0) {
+                        a.block_min_q[fw * a.n_blocks + blk] = bs;
+                        if (a.block_arg) a.block_arg[fw * a.n_blocks + blk] = bi;
+                    }
+                }
+            }
+        }
+        __syncthreads();  // all partial minima written; all LUT reads done
+        // ---- outputs (each warp finishes its own frame) ---------------------------------------------------
+        if (active) {
+            if (!BLOCKS) {
+                long long best_s = S.red_s[warp][0];
+                int best_i = S.red_i[warp][0];
+#pragma unroll
+                for (int v = 1; v < OSD_FPB; ++v) {
+                    const long long os = S.red_s[warp][v];
+                    const int oi = S.red_i[warp][v];
+                    if (os < best_s || (os == best_s && oi < best_i)) { best_s = os; best_i = oi; }
+                }
+                // re-encode the winner and un-permute
+                unsigned long long D = d0, flip = 0ull;
+                if (best_i != 0x7fffffff) {
+                    const unsigned tw = __ldg(a.teps + best_i);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const unsigned t = (tw >> (8 * j)) & 0xffu;
+                        if (t < 64u) { D ^= F.prow[t]; flip ^= 1ull << t; }
+                    }
+                }
+                const unsigned long long c_lrb = D ^ hd_lrb;
+                const unsigned long long c_mrb = ho_mrb ^ flip;
+                F.tmp[pm[0]] = (unsigned char)((c_mrb >> lane) & 1ull);
+                F.tmp[pm[1]] = (unsigned char)((c_mrb >> (lane + 32)) & 1ull);
+                F.tmp[pm[2]] = (unsigned char)((c_lrb >> lane) & 1ull);
+                F.tmp[pm[3]] = (unsigned char)((c_lrb >> (lane + 32)) & 1ull);
+                __syncwarp();
+                unsigned wout[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) wout[k] = __ballot_sync(0xffffffffu, F.tmp[lane + 32 * k]);
+                const int64_t orow = a.idx ? row : f;
+                if (lane < 4 && a.cw_bits) {
+                    const unsigned wv = lane == 0 ? wout[0] : lane == 1 ? wout[1] : lane == 2 ? wout[2] : wout[3];
+                    a.cw_bits[orow * 4 + lane] = wv;
+                }
                 if (lane == 0) {
-                    a.block_min_q[f * nblk + blk] = bs;
-                    if (a.block_arg) a.block_arg[f * nblk + blk] = bi;
+                    if (a.best_tep) a.best_tep[orow] = best_i;
+                    if (a.best_score_q) a.best_score_q[orow] = best_s;
                 }
             }
-            if (bs < best_s || (bs == best_s && bi < best_i)) { best_s = bs; best_i = bi; }
-        }
-        // ---- outputs -----------------------------------------------------------------------------
-        if (!BLOCKS || a.cw_bits) {
-            // re-encode the winner and un-permute
-            unsigned long long D = d0, flip = 0ull;
-            if (best_i != 0x7fffffff) {
-                const unsigned w = __ldg(a.teps + best_i);
+            if (lane == 0 && a.score_exp) a.score_exp[f] = E;
+            if (a.perm) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const unsigned t = (w >> (8 * j)) & 0xffu;
-                    if (t < 64u) { D ^= S.prow[t]; flip ^= 1ull << t; }
-                }
+                for (int k = 0; k < 4; ++k) a.perm[f * N + lane + 32 * k] = pm[k];
             }
-            const unsigned long long c_lrb = D ^ hd_lrb;
-            const unsigned long long c_mrb = ho_mrb ^ flip;
-            S.tmp[pm[0]] = (unsigned char)((c_mrb >> lane) & 1ull);
-            S.tmp[pm[1]] = (unsigned char)((c_mrb >> (lane + 32)) & 1ull);
-            S.tmp[pm[2]] = (unsigned char)((c_lrb >> lane) & 1ull);
-            S.tmp[pm[3]] = (unsigned char)((c_lrb >> (lane + 32)) & 1ull);
-            __syncwarp();
-            unsigned wout[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) wout[k] = __ballot_sync(0xffffffffu, S.tmp[lane + 32 * k]);
-            const int64_t orow = a.idx ? row : f;
-            if (lane < 4 && a.cw_bits) {
-                const unsigned wv = lane == 0 ? wout[0] : lane == 1 ? wout[1] : lane == 2 ? wout[2] : wout[3];
-                a.cw_bits[orow * 4 + lane] = wv;
-            }
-            if (lane == 0) {
-                if (a.best_tep) a.best_tep[orow] = best_i;
-                if (a.best_score_q) a.best_score_q[orow] = best_s;
+            if (a.redG) {
+                a.redG[f * K + lane] = myprow[0];
+                a.redG[f * K + lane + 32] = myprow[1];
             }
         }
-        if (lane == 0 && a.score_exp) a.score_exp[f] = E;
-        if (a.perm) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) a.perm[f * N + lane + 32 * k] = pm[k];
-        }
-        if (a.redG) {
-            a.redG[f * K + lane] = myprow[0];
-            a.redG[f * K + lane + 32] = myprow[1];
-        }
+        // the next round's prepare overwrites fr[] and red_*: every warp has passed the barrier above and
+        // only touches its own FrameSm until the next barrier
     }
 }
 
 template <int MAXW, bool BLOCKS>
 static int launch_variant(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st) {
     auto kern = osd_kernel<MAXW, BLOCKS>;
-    const int smem = OSD_WARPS * (int)sizeof(OsdSmem);
+    const int smem = (int)sizeof(OsdSmem);
     static thread_local int occ_cache[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int& occ = occ_cache[h->device & 7];
     if (occ == 0) {
@@ -368,7 +466,7 @@ static int launch_variant(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st) {
         LDPCB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, OSD_THREADS, smem));
         if (occ < 1) occ = 1;
     }
-    int64_t want = (a.B + OSD_WARPS - 1) / OSD_WARPS;
+    int64_t want = (a.B + OSD_FPB - 1) / OSD_FPB;
     int64_t cap = (int64_t)h->sm_count * occ;
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
