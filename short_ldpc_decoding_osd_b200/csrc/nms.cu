@@ -27,7 +27,8 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
     return r;
 }
 
-template <int DVA, int DVB, bool TRAJ, bool EARLY>
+// REG8: every check has degree 8 (CCSDS): edge e of check c is stored at CV[e*64+c], no padding slots needed
+template <int DVA, int DVB, bool REG8, bool TRAJ, bool EARLY>
 __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(NmsArgs a, const NmsTables* __restrict__ tab) {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31;
@@ -37,7 +38,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(NmsArgs a, const NmsTa
 
     // ---- per-lane graph tables (registers) ----
     int tv[2][DC];  // T index of edge e of check lane+32q
-    int cs[2][DC];  // CV index where that edge's message is stored
+    int cs[2][REG8 ? 1 : DC];  // CV index where that edge's message is stored (computed when REG8)
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         const int c = lane + 32 * q;
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(NmsArgs a, const NmsTa
         for (int e = 0; e < DC; ++e) {
             const int v = tab->chk_var[c][e];
             tv[q][e] = v;
-            cs[q][e] = (v < N) ? (e * M + c) : 513;
+            if (!REG8) cs[q][e] = (v < N) ? (e * M + c) : 513;
         }
     }
     int vs[4][DVA > DVB ? DVA : DVB];
@@ -56,10 +57,12 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(NmsArgs a, const NmsTa
         for (int d = 0; d < (k < 2 ? DVA : DVB); ++d) vs[k][d] = tab->var_slot[v][d];
     }
     uint32_t mk[2][4];
+    if (EARLY) {  // syndrome masks stay in registers only when they are needed every iteration
 #pragma unroll
-    for (int q = 0; q < 2; ++q)
+        for (int q = 0; q < 2; ++q)
 #pragma unroll
-        for (int w = 0; w < 4; ++w) mk[q][w] = tab->chk_mask[lane + 32 * q][w];
+            for (int w = 0; w < 4; ++w) mk[q][w] = tab->chk_mask[lane + 32 * q][w];
+    }
 
     if (lane == 0) {
         T[128] = __int_as_float(0x7f800000);  // +inf feeds padded check edges
@@ -106,32 +109,40 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(NmsArgs a, const NmsTa
             // ---- check phase: vc = T - cv_old, min1/min2/sign, new cv ----
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                float x[DC];
-#pragma unroll
-                for (int e = 0; e < DC; ++e) x[e] = __fsub_rn(T[tv[q][e]], cvo[q][e]);
-                float m1 = __int_as_float(0x7f800000), m2 = m1;
-                uint32_t sx = 0;
-                bool z = false;
+                float x[DC], ax[DC];
 #pragma unroll
                 for (int e = 0; e < DC; ++e) {
-                    const float ax = fabsf(x[e]);
-                    m2 = fminf(m2, fmaxf(m1, ax));
-                    m1 = fminf(m1, ax);
-                    sx ^= __float_as_uint(x[e]);
-                    z |= (x[e] == 0.0f);
+                    x[e] = __fsub_rn(T[tv[q][e]], cvo[q][e]);
+                    ax[e] = fabsf(x[e]);
                 }
+                // two smallest magnitudes (duplicates kept, like tf.nn.top_k) by a tournament of sorted pairs
+                float lo[4], hi[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    lo[i] = fminf(ax[2 * i], ax[2 * i + 1]);
+                    hi[i] = fmaxf(ax[2 * i], ax[2 * i + 1]);
+                }
+                const float l01 = fminf(lo[0], lo[1]), h01 = fminf(fmaxf(lo[0], lo[1]), fminf(hi[0], hi[1]));
+                const float l23 = fminf(lo[2], lo[3]), h23 = fminf(fmaxf(lo[2], lo[3]), fminf(hi[2], hi[3]));
+                float m1 = fminf(l01, l23);
+                float m2 = fminf(fmaxf(l01, l23), fminf(h01, h23));
                 m1 = fminf(m1, 1e30f);  // tf.clip_by_value(|vc|, 0, 1e30), ms_test.py:196
                 m2 = fminf(m2, 1e30f);
-                const float a1 = __fmul_rn(a.alpha, m1);
-                const float a2 = __fmul_rn(a.alpha, m2);
+                // tf.sign(0) = 0 zeroes every message of the check (ms_test.py:187-191); some |vc| is 0 iff min1 is 0
+                const bool z = (m1 == 0.0f);
+                const float a1 = z ? 0.0f : __fmul_rn(a.alpha, m1);
+                const float a2 = z ? 0.0f : __fmul_rn(a.alpha, m2);
+                unsigned sx = __float_as_uint(x[0]);
+#pragma unroll
+                for (int e = 1; e < DC; ++e) sx ^= __float_as_uint(x[e]);
                 sx &= 0x80000000u;
+                const unsigned u1 = __float_as_uint(a1) ^ sx, u2 = __float_as_uint(a2) ^ sx;
 #pragma unroll
                 for (int e = 0; e < DC; ++e) {
-                    const float mag = (fabsf(x[e]) > m1) ? a1 : a2;
-                    float o = __uint_as_float(__float_as_uint(mag) ^ sx ^ (__float_as_uint(x[e]) & 0x80000000u));
-                    o = z ? 0.0f : o;  // tf.sign(0) = 0 zeroes the whole check (ms_test.py:187-191)
+                    const unsigned u = (ax[e] > m1) ? u1 : u2;  // strict '>' (ms_test.py:206)
+                    const float o = __uint_as_float(u ^ (__float_as_uint(x[e]) & 0x80000000u));
                     cvo[q][e] = o;
-                    CV[cs[q][e]] = o;
+                    CV[REG8 ? (e * M + lane + 32 * q) : cs[q][e]] = o;
                 }
             }
             __syncwarp();
@@ -144,7 +155,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(NmsArgs a, const NmsTa
                 soft[k] = __fadd_rn(S, __fmul_rn(a.w_marg, y[k]));
                 T[lane + 32 * k] = same_w ? soft[k] : __fadd_rn(S, __fmul_rn(a.w_vc, y[k]));
                 if (TRAJ) a.soft_traj[(f * rows + it + 1) * N + lane + 32 * k] = soft[k];
-                hw[k] = __ballot_sync(0xffffffffu, !(soft[k] > 0.0f));
+                if (EARLY) hw[k] = __ballot_sync(0xffffffffu, !(soft[k] > 0.0f));
             }
             it_used = it + 1;
             __syncwarp();
@@ -160,6 +171,14 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(NmsArgs a, const NmsTa
             for (int it = it_used; it < a.iters; ++it)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) a.soft_traj[(f * rows + it + 1) * N + lane + 32 * k] = soft[k];
+        }
+        if (!EARLY) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) hw[k] = __ballot_sync(0xffffffffu, !(soft[k] > 0.0f));
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int w = 0; w < 4; ++w) mk[q][w] = __ldg(&tab->chk_mask[lane + 32 * q][w]);
         }
         uint32_t par = 0;
 #pragma unroll
@@ -177,9 +196,9 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(NmsArgs a, const NmsTa
     }
 }
 
-template <int DVA, int DVB, bool TRAJ, bool EARLY>
+template <int DVA, int DVB, bool REG8, bool TRAJ, bool EARLY>
 static int launch_variant(ldpcb_handle* h, const NmsArgs& a, cudaStream_t st) {
-    auto kern = nms_kernel<DVA, DVB, TRAJ, EARLY>;
+    auto kern = nms_kernel<DVA, DVB, REG8, TRAJ, EARLY>;
     const int smem = NMS_WARPS * NMS_FRAME_FLOATS * (int)sizeof(float);
     static thread_local int occ_cache[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int& occ = occ_cache[h->device & 7];
@@ -196,17 +215,19 @@ static int launch_variant(ldpcb_handle* h, const NmsArgs& a, cudaStream_t st) {
     return LDPCB_OK;
 }
 
-template <int DVA, int DVB>
+template <int DVA, int DVB, bool REG8>
 static int launch_deg(ldpcb_handle* h, const NmsArgs& a, cudaStream_t st) {
     const bool traj = a.soft_traj != nullptr, early = a.early_stop != 0;
-    if (traj) return early ? launch_variant<DVA, DVB, true, true>(h, a, st) : launch_variant<DVA, DVB, true, false>(h, a, st);
-    return early ? launch_variant<DVA, DVB, false, true>(h, a, st) : launch_variant<DVA, DVB, false, false>(h, a, st);
+    if (traj) return early ? launch_variant<DVA, DVB, REG8, true, true>(h, a, st) : launch_variant<DVA, DVB, REG8, true, false>(h, a, st);
+    return early ? launch_variant<DVA, DVB, REG8, false, true>(h, a, st) : launch_variant<DVA, DVB, REG8, false, false>(h, a, st);
 }
 
 int launch_nms(ldpcb_handle* h, const NmsArgs& a, cudaStream_t st) {
     if (a.B == 0) return LDPCB_OK;
-    if (h->nms_host.max_var_deg_lo <= 5 && h->nms_host.max_var_deg_hi <= 3) return launch_deg<5, 3>(h, a, st);
-    return launch_deg<DV, DV>(h, a, st);
+    bool reg8 = true;
+    for (int c = 0; c < M; ++c) reg8 = reg8 && h->nms_host.chk_var[c][DC - 1] < N;
+    if (reg8 && h->nms_host.max_var_deg_lo <= 5 && h->nms_host.max_var_deg_hi <= 3) return launch_deg<5, 3, true>(h, a, st);
+    return launch_deg<DV, DV, false>(h, a, st);
 }
 
 }  // namespace ldpcb
