@@ -201,6 +201,42 @@ int ldpcb_osd_block_minima(ldpcb_t* h, const float* order_llr_dev, const float* 
                            int32_t* score_exp_dev, const uint32_t* truth_bits_dev,
                            int64_t* truth_score_q_dev, uint8_t* perm_dev, void* stream);
 
+/*
+ * Sweep only, host buffers: the frames are already permuted (64 MRB positions first) and come with the
+ * 64 P' words of their systematic generator [I | P'].  Replaces convention_osd_main(wrapped_input)
+ * (FS_OSD/convention_osd.py:49-77; PB_OSD/convention_osd.py:49-77 for the 6-tuple form) when the caller
+ * brings its own updated_inputs / reduced_G / error_patterns_matrix, e.g. from swapped_info.
+ *   upd_order_llr_host [B,128] permuted ordering metric (MRB hard decisions), upd_score_llr_host [B,128]
+ *   permuted scoring metric (may alias), redG_host [B,64] uint64, teps_host [n_teps] packed TEPs
+ *   cw_bits_host [B,4] out: best codeword in the PERMUTED order of the inputs
+ */
+int ldpcb_osd_sweep_host(ldpcb_t* h, const float* upd_order_llr_host, const float* upd_score_llr_host,
+                         const uint64_t* redG_host, int64_t B, const uint32_t* teps_host, int32_t n_teps, int flags,
+                         uint32_t* cw_bits_host, int32_t* best_tep_host, int64_t* best_score_q_host,
+                         int32_t* score_exp_host);
+
+/*
+ * FS-OSD (fast and scalable OSD) policy on top of the same sort / elimination / sweep machinery.
+ * Replaces the per-frame body of fs_osd(snr, beta, selected_ds) (FS_OSD/fs_testing.py:94-165):
+ * order-0 acceptance below tau_e (:131-135), order-skip rule with beta (:22-30,137-139), per-TEP
+ * tau_e stop -- which does not update the decision, as in the reference (:143-147) -- and tau_psc
+ * gated improvement (:148-152), TEPs in generate_sequential_teps order (:32-49).
+ *   llr_dev [B,128] channel LLR of the frames (row 0 of the retest record, fs_testing.py:98-99)
+ *   order_limit 0..3; tau_e = floor(d_min-1)/2 = 6.5 for d_min 14 (fs_testing.py:92); tau_psc 30;
+ *   beta_shift = beta*(n-k) (6.4 for beta 0.1)
+ *   cw_bits_dev [B,4] out: optimal_codeword, original bit positions
+ *   best_tep_dev [B] out (may be NULL): its index in the FS enumeration
+ *   num_teps_dev [B] out (may be NULL): TEPs visited (the reference's num_teps, :130,142)
+ *   stop_kind_dev [B] out (may be NULL): 0 order-0 accepted, 1 tau_e stop, 2 skip rule, 3 all orders swept
+ */
+int ldpcb_osd_fs_decode(ldpcb_t* h, const float* llr_dev, int64_t B, int order_limit, float tau_e, int tau_psc,
+                        float beta_shift, uint32_t* cw_bits_dev, int32_t* best_tep_dev, int32_t* num_teps_dev,
+                        uint8_t* stop_kind_dev, int64_t* best_score_q_dev, int32_t* score_exp_dev,
+                        uint8_t* perm_dev, void* stream);
+int ldpcb_osd_fs_decode_host(ldpcb_t* h, const float* llr_host, int64_t B, int order_limit, float tau_e, int tau_psc,
+                             float beta_shift, uint32_t* cw_bits_host, int32_t* best_tep_host, int32_t* num_teps_host,
+                             uint8_t* stop_kind_host);
+
 /* Number of TEPs of an enumeration (1, 65, 2081, 43745 for order 0..3), or a negative status. */
 int ldpcb_tep_count(ldpcb_t* h, int order, int tep_order);
 /* Copy the enumeration to the host in the packed format described above (n = ldpcb_tep_count). */

@@ -303,3 +303,77 @@ def convention_osd_main(updated_inputs, updated_labels, reduced_G, teps, boundar
                 phase = i
                 break
     return ok, len(teps), phase, idx
+
+
+# ---- FS-OSD policy -----------------------------------------------------------------------------------------
+def fs_frame(y, G, order_limit: int, tau_e: float = 6.5, tau_psc: int = 30, beta: float = 0.1, labels=None):
+    """One frame of fs_osd (FS_OSD/fs_testing.py:94-165) with the exact integer score.
+
+    Returns dict(codeword[128] original positions, best_tep (index in generate_teps_fs order), num_teps,
+    stop_kind: 0 order-0 accepted / 1 tau_e stop / 2 skip rule / 3 all orders swept, success if labels given).
+    The reference compares fp32 sums; here boundary, beta*(n-k) and w_dmin live in the frame's integer
+    score units (beta*(n-k) is first rounded to fp32 as in `x + beta*(n-k)` with x an fp32 tensor).
+    """
+    y = np.asarray(y, dtype=np.float32)
+    _, _, reduced_G, perm = swapped_info(y, np.zeros(N, dtype=np.int64), G)
+    yp = y[perm]
+    q, E = quantize(yp)
+    h = hard_of(yp)
+    rows = [int("".join(str(int(b)) for b in reduced_G[t][::-1]), 2) for t in range(K)]
+    h_int = int("".join(str(int(b)) for b in h[::-1]), 2)
+    qs = [int(v) for v in q]
+    c0 = 0
+    for t in range(K):
+        if h[t]:
+            c0 ^= rows[t]
+
+    def evaluate(tep):
+        cw = c0
+        for p in tep:
+            cw ^= rows[p]
+        d = cw ^ h_int
+        hd = bin(d).count("1")
+        s = 0
+        dd = d
+        while dd:
+            low = dd & -dd
+            s += qs[low.bit_length() - 1]
+            dd ^= low
+        return cw, hd, s
+
+    shift = float(np.float32(beta * (N - K)))
+    sh = np.ldexp(np.float64(shift), 54 - E)
+    shift_q = (1 << 62) if sh >= 4.6e18 else int(np.rint(sh))
+    teps = generate_teps_fs(order_limit)
+    cls = [0, 1, 65, 2081, 43745]
+    opt_cw, hd0, w_dmin = evaluate(())
+    best, num, kind = 0, 1, 3
+    if hd0 < tau_e:
+        kind = 0
+    else:
+        bnd = 0
+        stop = False
+        for j in range(order_limit):
+            bnd += qs[63 - j]
+            if not (bnd + shift_q < w_dmin):
+                kind = 2
+                break
+            for i in range(cls[j + 1], cls[j + 2]):
+                num += 1
+                cw, hd, s = evaluate(teps[i])
+                if hd < tau_e:
+                    stop = True
+                    kind = 1
+                    break
+                if hd < tau_psc and s < w_dmin:
+                    w_dmin, opt_cw, best = s, cw, i
+            if stop:
+                break
+    cw_perm = np.array([(opt_cw >> t) & 1 for t in range(N)], dtype=np.uint8)
+    codeword = np.zeros(N, dtype=np.uint8)
+    codeword[perm] = cw_perm
+    out = {"codeword": codeword, "best_tep": best, "num_teps": num, "stop_kind": kind, "best_score_q": w_dmin, "score_exp": E,
+           "perm": perm.astype(np.uint8)}
+    if labels is not None:
+        out["success"] = bool(np.array_equal(codeword, np.asarray(labels).astype(np.uint8)))
+    return out

@@ -135,6 +135,17 @@ struct OsdArgs {
 };
 int launch_osd(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st);
 
+// FS-OSD policy parameters (FS_OSD/fs_testing.py:92,129-160)
+struct FsParams {
+    float tau_e;
+    int tau_psc;
+    float beta_shift;  // beta * (n - k) as the reference adds it to an fp32 sum
+    int order;
+    int32_t* num_teps;
+    uint8_t* stop_kind;  // 0: order-0 accepted, 1: tau_e stop inside a sweep, 2: skip rule, 3: all orders swept
+};
+int launch_osd_fs(ldpcb_handle* h, const OsdArgs& a, const FsParams& fp, cudaStream_t st);
+
 int build_tep_tables(ldpcb_handle* h);
 
 }  // namespace ldpcb

@@ -41,6 +41,7 @@ struct __align__(16) FrameSm {
     float ys[N];                  // scoring metric
     unsigned long long d0;        // order-0 discrepancy on the LRB
     long long base;               // order-0 discrepancy weight on the MRB
+    unsigned long long d0m;       // order-0 discrepancy bits on the MRB (0 when both metrics agree)
     unsigned char pi1[N];         // sorted position -> original index
     unsigned char pos[N];         // permuted position (MRB then LRB) -> sorted position
     unsigned char prow_of[K];     // pivot row of MRB position t
@@ -52,6 +53,9 @@ struct __align__(16) OsdSmem {
     FrameSm fr[OSD_FPB];
     long long red_s[OSD_FPB][OSD_FPB];  // [frame][warp] partial minima
     int red_i[OSD_FPB][OSD_FPB];
+    int red_stop[OSD_FPB];           // FS: per-warp first stopping TEP index
+    long long fs_score[OSD_FPB];     // FS results per frame
+    int fs_opt[OSD_FPB], fs_num[OSD_FPB], fs_kind[OSD_FPB];
 };
 
 __device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) {
@@ -149,6 +153,193 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned (&key)[4], unsigned (
     }
 }
 
+// Registers a warp keeps about its frame between prepare and output.
+struct Prep {
+    unsigned char pm[4];            // original index of permuted positions lane, lane+32 (MRB), lane+64, lane+96 (LRB)
+    unsigned long long myprow[2];   // P' rows of MRB positions lane, lane+32
+    unsigned long long hd_lrb;      // hard decisions the discrepancy is measured against, LRB part
+    unsigned long long hd_mrb;      // same, MRB part
+    unsigned long long ho_mrb;      // MRB hard decisions of the ordering metric (order-0 information bits)
+    unsigned long long d0;          // order-0 discrepancy on the LRB
+    int E;                          // score exponent
+};
+
+// Steps 1-4 for one frame by one warp; fills F (prow, qd, qlrb, d0, base) and returns the registers above.
+template <bool TRUTH>
+__device__ __forceinline__ Prep prepare_frame(const OsdArgs& a, FrameSm& F, const uint64_t* __restrict__ gcol, int64_t row,
+                                              int64_t f, int lane, bool ties_high, bool disc_from_score) {
+    unsigned long long* cols = reinterpret_cast<unsigned long long*>(F.qd);  // [128], dead before qd/qlrb are written
+    unsigned char pm[4] = {0, 0, 0, 0};
+    unsigned long long myprow[2] = {0ull, 0ull};
+    unsigned long long hd_lrb = 0ull, ho_mrb = 0ull, d0 = 0ull;
+    int E = 0;
+    // ---- load ---------------------------------------------------------------------------
+    const float4 v = reinterpret_cast<const float4*>(a.order_llr + row * N)[lane];
+    reinterpret_cast<float4*>(F.yo)[lane] = v;
+    reinterpret_cast<float4*>(F.ys)[lane] = reinterpret_cast<const float4*>(a.score_llr + row * N)[lane];
+    if (a.redG_in) {
+        // pre-permuted frame with its systematic generator rows (convention_osd_main's inputs)
+        myprow[0] = a.redG_in[row * K + lane];
+        myprow[1] = a.redG_in[row * K + lane + 32];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pm[k] = (unsigned char)(lane + 32 * k);
+        __syncwarp();
+    } else {
+        // ---- 1. sort --------------------------------------------------------------------
+        unsigned key[4] = {__float_as_uint(v.x) & 0x7fffffffu, __float_as_uint(v.y) & 0x7fffffffu,
+                           __float_as_uint(v.z) & 0x7fffffffu, __float_as_uint(v.w) & 0x7fffffffu};
+        unsigned idx[4] = {4u * lane, 4u * lane + 1, 4u * lane + 2, 4u * lane + 3};
+        bitonic_sort_desc(key, idx, lane);
+        const unsigned nxt = __shfl_down_sync(0xffffffffu, key[0], 1);
+        const bool tie = (key[0] == key[1]) || (key[1] == key[2]) || (key[2] == key[3]) || (lane < 31 && key[3] == nxt);
+        if (__any_sync(0xffffffffu, tie)) {
+            // exact rank sort with the tf.argsort tie rule (stable: lower index first; reversed-ascending: higher first)
+            __syncwarp();
+            unsigned mykey[4];
+            int rank[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mykey[k] = __float_as_uint(F.yo[4 * lane + k]) & 0x7fffffffu;
+            for (int i = 0; i < N; ++i) {
+                const unsigned ki = __float_as_uint(F.yo[i]) & 0x7fffffffu;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int j = 4 * lane + k;
+                    const bool first = ties_high ? (i > j) : (i < j);
+                    rank[k] += (ki > mykey[k]) || (ki == mykey[k] && first);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) F.pi1[rank[k]] = (unsigned char)(4 * lane + k);
+            __syncwarp();
+            const unsigned w = reinterpret_cast<const unsigned*>(F.pi1)[lane];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) idx[k] = (w >> (8 * k)) & 0xffu;
+        } else {
+            reinterpret_cast<unsigned*>(F.pi1)[lane] = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
+        }
+        // ---- 2. GF(2) elimination, column-major ----------------------------------------------
+        unsigned long long col[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) col[k] = gcol[idx[k]];
+        {
+            unsigned long long used = 0ull;
+            int npiv = 0, nlrb = 0;
+            for (int l = 0; l < 32; ++l) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int c = 4 * l + k;
+                    if (npiv == K) {  // basis complete: everything left is LRB
+                        if (lane == 0) F.pos[K + nlrb] = (unsigned char)c;
+                        ++nlrb;
+                        continue;
+                    }
+                    const unsigned long long cc = shfl64(col[k], l);
+                    const unsigned long long cand = cc & ~used;
+                    if (cand == 0ull) {  // dependent on more reliable columns
+                        if (lane == 0) F.pos[K + nlrb] = (unsigned char)c;
+                        ++nlrb;
+                        continue;
+                    }
+                    const int p = __ffsll((long long)cand) - 1;
+                    used |= 1ull << p;
+                    if (lane == 0) { F.pos[npiv] = (unsigned char)c; F.prow_of[npiv] = (unsigned char)p; }
+                    ++npiv;
+                    const unsigned long long m = cc ^ (1ull << p);
+                    if (m != 0ull) {  // an untouched unit column (an information position of G) needs no row operation
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            if ((col[kk] >> p) & 1ull) col[kk] ^= m;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cols[4 * lane + k] = col[k];
+        __syncwarp();
+        // ---- permutation pi2 o pi1 -----------------------------------------------------------
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pm[k] = F.pi1[F.pos[lane + 32 * k]];
+        // ---- 3. P' rows: 64x64 bit transpose of the LRB columns -------------------------------
+        const unsigned long long ca = cols[F.pos[K + lane]];
+        const unsigned long long cb = cols[F.pos[K + 32 + lane]];
+        const unsigned tA = transpose32((unsigned)ca, lane);          // rows 0..31,  LRB cols 0..31
+        const unsigned tB = transpose32((unsigned)(ca >> 32), lane);  // rows 32..63, LRB cols 0..31
+        const unsigned tC = transpose32((unsigned)cb, lane);          // rows 0..31,  LRB cols 32..63
+        const unsigned tD = transpose32((unsigned)(cb >> 32), lane);  // rows 32..63, LRB cols 32..63
+        __syncwarp();  // all reads of cols are done; reuse it for the physical rows
+        unsigned long long* rowsP = cols;  // rows in physical order, first 512 B of the free cols area
+        rowsP[lane] = ((unsigned long long)tC << 32) | tA;
+        rowsP[lane + 32] = ((unsigned long long)tD << 32) | tB;
+        __syncwarp();
+        myprow[0] = rowsP[F.prow_of[lane]];
+        myprow[1] = rowsP[F.prow_of[lane + 32]];
+        __syncwarp();  // rowsP dead before qd/qlrb are written below
+    }
+    // ---- 4. permuted metrics, exact reliabilities, order-0 codeword ----------------------------
+    float yo[4], ys[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { yo[k] = F.yo[pm[k]]; ys[k] = F.ys[pm[k]]; }
+    float as[4];
+    unsigned amax_bits = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        as[k] = score_abs(ys[k]);
+        amax_bits = max(amax_bits, __float_as_uint(as[k]));
+    }
+#pragma unroll
+    for (int m = 16; m; m >>= 1) amax_bits = max(amax_bits, __shfl_xor_sync(0xffffffffu, amax_bits, m));
+    frexpf(__uint_as_float(amax_bits), &E);
+    long long q[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q[k] = quantize(as[k], E);
+    unsigned ho[4], hd[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        ho[k] = !(yo[k] > 0.0f);  // hard decision: 1 iff !(y > 0)   (convention_osd.py:54)
+        hd[k] = disc_from_score ? (unsigned)!(ys[k] > 0.0f) : ho[k];
+    }
+    long long base = 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const unsigned d0m = ho[k] ^ hd[k];
+        F.qd[lane + 32 * k] = d0m ? -q[k] : q[k];
+        base += d0m ? q[k] : 0ll;
+    }
+    base = warp_sum_ll(base);
+    F.qlrb[lane] = (unsigned long long)q[2];
+    F.qlrb[lane + 32] = (unsigned long long)q[3];
+    F.prow[lane] = myprow[0];
+    F.prow[lane + 32] = myprow[1];
+    unsigned long long c0 = (ho[0] ? myprow[0] : 0ull) ^ (ho[1] ? myprow[1] : 0ull);
+    c0 = warp_xor_ull(c0);
+    hd_lrb = (unsigned long long)__ballot_sync(0xffffffffu, hd[2]) | ((unsigned long long)__ballot_sync(0xffffffffu, hd[3]) << 32);
+    ho_mrb = (unsigned long long)__ballot_sync(0xffffffffu, ho[0]) | ((unsigned long long)__ballot_sync(0xffffffffu, ho[1]) << 32);
+    const unsigned long long hd_mrb_out = (unsigned long long)__ballot_sync(0xffffffffu, hd[0]) | ((unsigned long long)__ballot_sync(0xffffffffu, hd[1]) << 32);
+    d0 = c0 ^ hd_lrb;
+    if (lane == 0) { F.d0 = d0; F.base = base; F.d0m = ho_mrb ^ hd_mrb_out; F.prow[64] = 0ull; F.qd[64] = 0ll; }  // [64]: padded TEP slots (qd aliases cols until here)
+    if (TRUTH && a.truth_bits && a.truth_score_q) {
+        long long ts = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned tb = (a.truth_bits[row * 4 + (pm[k] >> 5)] >> (pm[k] & 31)) & 1u;
+            ts += (tb ^ hd[k]) ? q[k] : 0ll;
+        }
+        ts = warp_sum_ll(ts);
+        if (lane == 0) a.truth_score_q[f] = ts;
+    }
+    Prep r;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r.pm[k] = pm[k];
+    r.myprow[0] = myprow[0];
+    r.myprow[1] = myprow[1];
+    r.hd_lrb = hd_lrb;
+    r.hd_mrb = hd_mrb_out;
+    r.ho_mrb = ho_mrb;
+    r.d0 = d0;
+    r.E = E;
+    return r;
+}
+
 template <int MAXW, bool BLOCKS>
 __global__ void __launch_bounds__(OSD_THREADS) osd_kernel(OsdArgs a, const uint64_t* __restrict__ gcol) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -157,8 +348,6 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_kernel(OsdArgs a, const uint6
     const int lane = tid & 31;
     const int warp = tid >> 5;
     FrameSm& F = S.fr[warp];
-    unsigned long long* cols = reinterpret_cast<unsigned long long*>(F.qd);  // [128], dead before qd/qlrb are written
-
     const int64_t nframes = a.count ? (int64_t)*a.count : a.B;
     const bool ties_high = (a.flags & LDPCB_OSD_TIES_HIGH_INDEX_FIRST) != 0;
     const bool disc_from_score = (a.flags & LDPCB_OSD_DISC_HARD_FROM_SCORE) != 0;
@@ -167,165 +356,12 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_kernel(OsdArgs a, const uint6
         const int64_t f = f0 + warp;
         const bool active = f < nframes;
         const int64_t row = active ? (a.idx ? (int64_t)a.idx[f] : f) : 0;
-        unsigned char pm[4] = {0, 0, 0, 0};
-        unsigned long long myprow[2] = {0ull, 0ull};
-        unsigned long long hd_lrb = 0ull, ho_mrb = 0ull, d0 = 0ull;
-        int E = 0;
-        if (active) {
-            // ---- load ---------------------------------------------------------------------------
-            const float4 v = reinterpret_cast<const float4*>(a.order_llr + row * N)[lane];
-            reinterpret_cast<float4*>(F.yo)[lane] = v;
-            reinterpret_cast<float4*>(F.ys)[lane] = reinterpret_cast<const float4*>(a.score_llr + row * N)[lane];
-            if (a.redG_in) {
-                // pre-permuted frame with its systematic generator rows (convention_osd_main's inputs)
-                myprow[0] = a.redG_in[row * K + lane];
-                myprow[1] = a.redG_in[row * K + lane + 32];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) pm[k] = (unsigned char)(lane + 32 * k);
-                __syncwarp();
-            } else {
-                // ---- 1. sort --------------------------------------------------------------------
-                unsigned key[4] = {__float_as_uint(v.x) & 0x7fffffffu, __float_as_uint(v.y) & 0x7fffffffu,
-                                   __float_as_uint(v.z) & 0x7fffffffu, __float_as_uint(v.w) & 0x7fffffffu};
-                unsigned idx[4] = {4u * lane, 4u * lane + 1, 4u * lane + 2, 4u * lane + 3};
-                bitonic_sort_desc(key, idx, lane);
-                const unsigned nxt = __shfl_down_sync(0xffffffffu, key[0], 1);
-                const bool tie = (key[0] == key[1]) || (key[1] == key[2]) || (key[2] == key[3]) || (lane < 31 && key[3] == nxt);
-                if (__any_sync(0xffffffffu, tie)) {
-                    // exact rank sort with the tf.argsort tie rule (stable: lower index first; reversed-ascending: higher first)
-                    __syncwarp();
-                    unsigned mykey[4];
-                    int rank[4] = {0, 0, 0, 0};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) mykey[k] = __float_as_uint(F.yo[4 * lane + k]) & 0x7fffffffu;
-                    for (int i = 0; i < N; ++i) {
-                        const unsigned ki = __float_as_uint(F.yo[i]) & 0x7fffffffu;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int j = 4 * lane + k;
-                            const bool first = ties_high ? (i > j) : (i < j);
-                            rank[k] += (ki > mykey[k]) || (ki == mykey[k] && first);
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) F.pi1[rank[k]] = (unsigned char)(4 * lane + k);
-                    __syncwarp();
-                    const unsigned w = reinterpret_cast<const unsigned*>(F.pi1)[lane];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) idx[k] = (w >> (8 * k)) & 0xffu;
-                } else {
-                    reinterpret_cast<unsigned*>(F.pi1)[lane] = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
-                }
-                // ---- 2. GF(2) elimination, column-major ----------------------------------------------
-                unsigned long long col[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) col[k] = gcol[idx[k]];
-                {
-                    unsigned long long used = 0ull;
-                    int npiv = 0, nlrb = 0;
-                    for (int l = 0; l < 32; ++l) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int c = 4 * l + k;
-                            if (npiv == K) {  // basis complete: everything left is LRB
-                                if (lane == 0) F.pos[K + nlrb] = (unsigned char)c;
-                                ++nlrb;
-                                continue;
-                            }
-                            const unsigned long long cc = shfl64(col[k], l);
-                            const unsigned long long cand = cc & ~used;
-                            if (cand == 0ull) {  // dependent on more reliable columns
-                                if (lane == 0) F.pos[K + nlrb] = (unsigned char)c;
-                                ++nlrb;
-                                continue;
-                            }
-                            const int p = __ffsll((long long)cand) - 1;
-                            used |= 1ull << p;
-                            if (lane == 0) { F.pos[npiv] = (unsigned char)c; F.prow_of[npiv] = (unsigned char)p; }
-                            ++npiv;
-                            const unsigned long long m = cc ^ (1ull << p);
-                            if (m != 0ull) {  // an untouched unit column (an information position of G) needs no row operation
-#pragma unroll
-                                for (int kk = 0; kk < 4; ++kk)
-                                    if ((col[kk] >> p) & 1ull) col[kk] ^= m;
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) cols[4 * lane + k] = col[k];
-                __syncwarp();
-                // ---- permutation pi2 o pi1 -----------------------------------------------------------
-#pragma unroll
-                for (int k = 0; k < 4; ++k) pm[k] = F.pi1[F.pos[lane + 32 * k]];
-                // ---- 3. P' rows: 64x64 bit transpose of the LRB columns -------------------------------
-                const unsigned long long ca = cols[F.pos[K + lane]];
-                const unsigned long long cb = cols[F.pos[K + 32 + lane]];
-                const unsigned tA = transpose32((unsigned)ca, lane);          // rows 0..31,  LRB cols 0..31
-                const unsigned tB = transpose32((unsigned)(ca >> 32), lane);  // rows 32..63, LRB cols 0..31
-                const unsigned tC = transpose32((unsigned)cb, lane);          // rows 0..31,  LRB cols 32..63
-                const unsigned tD = transpose32((unsigned)(cb >> 32), lane);  // rows 32..63, LRB cols 32..63
-                __syncwarp();  // all reads of cols are done; reuse it for the physical rows
-                unsigned long long* rowsP = cols;  // rows in physical order, first 512 B of the free cols area
-                rowsP[lane] = ((unsigned long long)tC << 32) | tA;
-                rowsP[lane + 32] = ((unsigned long long)tD << 32) | tB;
-                __syncwarp();
-                myprow[0] = rowsP[F.prow_of[lane]];
-                myprow[1] = rowsP[F.prow_of[lane + 32]];
-                __syncwarp();  // rowsP dead before qd/qlrb are written below
-            }
-            // ---- 4. permuted metrics, exact reliabilities, order-0 codeword ----------------------------
-            float yo[4], ys[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { yo[k] = F.yo[pm[k]]; ys[k] = F.ys[pm[k]]; }
-            float as[4];
-            unsigned amax_bits = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                as[k] = score_abs(ys[k]);
-                amax_bits = max(amax_bits, __float_as_uint(as[k]));
-            }
-#pragma unroll
-            for (int m = 16; m; m >>= 1) amax_bits = max(amax_bits, __shfl_xor_sync(0xffffffffu, amax_bits, m));
-            frexpf(__uint_as_float(amax_bits), &E);
-            long long q[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) q[k] = quantize(as[k], E);
-            unsigned ho[4], hd[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                ho[k] = !(yo[k] > 0.0f);  // hard decision: 1 iff !(y > 0)   (convention_osd.py:54)
-                hd[k] = disc_from_score ? (unsigned)!(ys[k] > 0.0f) : ho[k];
-            }
-            long long base = 0;
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const unsigned d0m = ho[k] ^ hd[k];
-                F.qd[lane + 32 * k] = d0m ? -q[k] : q[k];
-                base += d0m ? q[k] : 0ll;
-            }
-            base = warp_sum_ll(base);
-            F.qlrb[lane] = (unsigned long long)q[2];
-            F.qlrb[lane + 32] = (unsigned long long)q[3];
-            F.prow[lane] = myprow[0];
-            F.prow[lane + 32] = myprow[1];
-            unsigned long long c0 = (ho[0] ? myprow[0] : 0ull) ^ (ho[1] ? myprow[1] : 0ull);
-            c0 = warp_xor_ull(c0);
-            hd_lrb = (unsigned long long)__ballot_sync(0xffffffffu, hd[2]) | ((unsigned long long)__ballot_sync(0xffffffffu, hd[3]) << 32);
-            ho_mrb = (unsigned long long)__ballot_sync(0xffffffffu, ho[0]) | ((unsigned long long)__ballot_sync(0xffffffffu, ho[1]) << 32);
-            d0 = c0 ^ hd_lrb;
-            if (lane == 0) { F.d0 = d0; F.base = base; F.prow[64] = 0ull; F.qd[64] = 0ll; }  // [64]: padded TEP slots (qd aliases cols until here)
-            if (BLOCKS && a.truth_bits && a.truth_score_q) {
-                long long ts = 0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const unsigned tb = (a.truth_bits[row * 4 + (pm[k] >> 5)] >> (pm[k] & 31)) & 1u;
-                    ts += (tb ^ hd[k]) ? q[k] : 0ll;
-                }
-                ts = warp_sum_ll(ts);
-                if (lane == 0) a.truth_score_q[f] = ts;
-            }
-        }
+        Prep P = {};
+        if (active) P = prepare_frame<BLOCKS>(a, F, gcol, row, f, lane, ties_high, disc_from_score);
+        const unsigned char* pm = P.pm;
+        const unsigned long long* myprow = P.myprow;
+        const unsigned long long hd_lrb = P.hd_lrb, ho_mrb = P.ho_mrb, d0 = P.d0;
+        const int E = P.E;
         // ---- 5./6. sweep: the four warps share one LUT and take the frames in turn ----------------------
         const int nfr = (int)((nframes - f0) < OSD_FPB ? (nframes - f0) : OSD_FPB);
         for (int w = 0; w < nfr; ++w) {
@@ -455,6 +491,206 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_kernel(OsdArgs a, const uint6
     }
 }
 
+
+// ---- FS-OSD policy (Choi & Jeong 2019 as re-implemented by the reference) ------------------------------------
+// fs_osd, FS_OSD/fs_testing.py:129-165, per frame:
+//   order 0: accept at once if the Hamming distance of the order-0 codeword to the hard decision is < tau_e
+//   (:131-135); order j+1 is entered only if  sum of the j+1 least reliable MRB |y|  + beta*(n-k) < w_dmin
+//   (:22-30,137-139); inside an order TEPs are taken in FS order; a TEP whose codeword is closer than tau_e
+//   stops everything WITHOUT becoming the decision (the reference's quirk, :143-147,162); a TEP closer than
+//   tau_psc with a strictly smaller weighted distance becomes the decision (:148-152).
+// The sequential loop is restated as, per order: find the first stopping TEP by a parallel sweep; the decision
+// is the first minimum among the eligible TEPs before it.  Weighted distances are the exact integer scores.
+
+__device__ __forceinline__ void fs_eval(const OsdSmem& S, const FrameSm& G, unsigned tw, unsigned long long gd0, long long gbase,
+                                        unsigned long long d0m, long long& s, int& hd) {
+    unsigned long long D = gd0, flip = 0ull;
+    s = gbase;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const unsigned t = (tw >> (8 * j)) & 0xffu;
+        if (t < 64u) { D ^= G.prow[t]; s += G.qd[t]; flip |= 1ull << t; }
+    }
+#pragma unroll
+    for (int b = 0; b < 8; ++b) s += (long long)S.lut[b][(unsigned)(D >> (8 * b)) & 0xffu];
+    hd = __popcll(D) + __popcll(flip ^ d0m);
+}
+
+__global__ void __launch_bounds__(OSD_THREADS) osd_fs_kernel(OsdArgs a, FsParams fp, const uint64_t* __restrict__ gcol) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    OsdSmem& S = *reinterpret_cast<OsdSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    FrameSm& F = S.fr[warp];
+    const int64_t nframes = a.count ? (int64_t)*a.count : a.B;
+    const int cls_start[5] = {0, 1, 65, 2081, 43745};
+
+    for (int64_t f0 = (int64_t)blockIdx.x * OSD_FPB; f0 < nframes; f0 += (int64_t)gridDim.x * OSD_FPB) {
+        const int64_t f = f0 + warp;
+        const bool active = f < nframes;
+        const int64_t row = active ? (a.idx ? (int64_t)a.idx[f] : f) : 0;
+        Prep P = {};
+        if (active) {
+            P = prepare_frame<false>(a, F, gcol, row, f, lane, false, false);
+            if (lane == 0) {
+                const double sh = (double)fp.beta_shift * __hiloint2double((1023 + 54 - P.E) << 20, 0);
+                S.fs_score[warp] = sh >= 4.6e18 ? (1ll << 62) : __double2ll_rn(sh);
+            }
+        }
+        const int nfr = (int)((nframes - f0) < OSD_FPB ? (nframes - f0) : OSD_FPB);
+        for (int w = 0; w < nfr; ++w) {
+            const FrameSm& G = S.fr[w];
+            __syncthreads();
+            {
+                const int b = tid >> 4, lo = tid & 15;
+                unsigned long long wv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) wv[i] = G.qlrb[8 * b + i];
+                unsigned long long lsum = 0ull;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) lsum += ((lo >> i) & 1) ? wv[i] : 0ull;
+                unsigned long long e[16];
+                e[0] = lsum;
+#pragma unroll
+                for (int x = 1; x < 16; ++x) e[x] = e[x & (x - 1)] + wv[4 + (31 - __clz(x & -x))];
+#pragma unroll
+                for (int x = 0; x < 16; ++x) S.lut[b][x * 16 + lo] = e[x];
+            }
+            __syncthreads();
+            const unsigned long long gd0 = G.d0, d0m = G.d0m;
+            const long long gbase = G.base;
+            // order 0 (every thread computes it: uniform state without a broadcast)
+            long long w_dmin;
+            int hd0;
+            fs_eval(S, G, 0xffffffffu, gd0, gbase, d0m, w_dmin, hd0);
+            int opt = 0, num = 1, kind = 3;
+            if ((float)hd0 < fp.tau_e) {
+                kind = 0;
+            } else {
+                // beta*(n-k) in this frame's integer score units; the owner warp left it in fs_score[w]
+                const long long shift_q = S.fs_score[w];
+                long long bnd = 0;
+                for (int j = 0; j < fp.order; ++j) {
+                    const long long qv = G.qd[63 - j];
+                    bnd += qv < 0 ? -qv : qv;
+                    if (!(bnd + shift_q < w_dmin)) { kind = 2; break; }
+                    const int r0 = cls_start[j + 1], r1 = cls_start[j + 2];
+                    int first_stop = 0x7fffffff;
+                    long long bs = 0x7fffffffffffffffll;
+                    int bi = 0x7fffffff;
+                    for (int i = r0 + tid; i < r1; i += OSD_THREADS) {
+                        long long s;
+                        int hd;
+                        fs_eval(S, G, __ldg(a.teps + i), gd0, gbase, d0m, s, hd);
+                        if ((float)hd < fp.tau_e) first_stop = min(first_stop, i);
+                        if (hd < fp.tau_psc && s < bs) { bs = s; bi = i; }
+                    }
+                    warp_argmin(bs, bi);
+#pragma unroll
+                    for (int m = 16; m; m >>= 1) first_stop = min(first_stop, __shfl_xor_sync(0xffffffffu, first_stop, m));
+                    __syncthreads();  // previous use of the reduction slots is over
+                    if (lane == 0) { S.red_s[w][warp] = bs; S.red_i[w][warp] = bi; S.red_stop[warp] = first_stop; }
+                    __syncthreads();
+                    first_stop = min(min(S.red_stop[0], S.red_stop[1]), min(S.red_stop[2], S.red_stop[3]));
+                    if (first_stop == 0x7fffffff) {
+                        bs = S.red_s[w][0]; bi = S.red_i[w][0];
+#pragma unroll
+                        for (int v = 1; v < OSD_FPB; ++v) {
+                            const long long os = S.red_s[w][v];
+                            const int oi = S.red_i[w][v];
+                            if (os < bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
+                        }
+                        if (bs < w_dmin) { w_dmin = bs; opt = bi; }
+                        num += r1 - r0;
+                    } else {
+                        // second pass: the decision only sees the TEPs before the stopping one
+                        bs = 0x7fffffffffffffffll; bi = 0x7fffffff;
+                        for (int i = r0 + tid; i < first_stop; i += OSD_THREADS) {
+                            long long s;
+                            int hd;
+                            fs_eval(S, G, __ldg(a.teps + i), gd0, gbase, d0m, s, hd);
+                            if (hd < fp.tau_psc && s < bs) { bs = s; bi = i; }
+                        }
+                        warp_argmin(bs, bi);
+                        __syncthreads();
+                        if (lane == 0) { S.red_s[w][warp] = bs; S.red_i[w][warp] = bi; }
+                        __syncthreads();
+                        bs = S.red_s[w][0]; bi = S.red_i[w][0];
+#pragma unroll
+                        for (int v = 1; v < OSD_FPB; ++v) {
+                            const long long os = S.red_s[w][v];
+                            const int oi = S.red_i[w][v];
+                            if (os < bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
+                        }
+                        if (bs < w_dmin) { w_dmin = bs; opt = bi; }
+                        num += first_stop - r0 + 1;
+                        kind = 1;
+                        break;
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) { S.fs_score[w] = w_dmin; S.fs_opt[w] = opt; S.fs_num[w] = num; S.fs_kind[w] = kind; }
+        }
+        __syncthreads();
+        if (active) {
+            const int best_i = S.fs_opt[warp];
+            unsigned long long D = P.d0, flip = 0ull;
+            const unsigned tw = __ldg(a.teps + best_i);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned t = (tw >> (8 * j)) & 0xffu;
+                if (t < 64u) { D ^= F.prow[t]; flip ^= 1ull << t; }
+            }
+            const unsigned long long c_lrb = D ^ P.hd_lrb;
+            const unsigned long long c_mrb = P.ho_mrb ^ flip;
+            F.tmp[P.pm[0]] = (unsigned char)((c_mrb >> lane) & 1ull);
+            F.tmp[P.pm[1]] = (unsigned char)((c_mrb >> (lane + 32)) & 1ull);
+            F.tmp[P.pm[2]] = (unsigned char)((c_lrb >> lane) & 1ull);
+            F.tmp[P.pm[3]] = (unsigned char)((c_lrb >> (lane + 32)) & 1ull);
+            __syncwarp();
+            unsigned wout[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) wout[k] = __ballot_sync(0xffffffffu, F.tmp[lane + 32 * k]);
+            const int64_t orow = a.idx ? row : f;
+            if (lane < 4 && a.cw_bits) {
+                const unsigned wv = lane == 0 ? wout[0] : lane == 1 ? wout[1] : lane == 2 ? wout[2] : wout[3];
+                a.cw_bits[orow * 4 + lane] = wv;
+            }
+            if (lane == 0) {
+                if (a.best_tep) a.best_tep[orow] = best_i;
+                if (a.best_score_q) a.best_score_q[orow] = S.fs_score[warp];
+                if (a.score_exp) a.score_exp[f] = P.E;
+                if (fp.num_teps) fp.num_teps[orow] = S.fs_num[warp];
+                if (fp.stop_kind) fp.stop_kind[orow] = (uint8_t)S.fs_kind[warp];
+            }
+            if (a.perm) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) a.perm[f * N + lane + 32 * k] = P.pm[k];
+            }
+        }
+        __syncthreads();  // fs_* consumed before the next round's sweeps rewrite them
+    }
+}
+
+int launch_osd_fs(ldpcb_handle* h, const OsdArgs& a, const FsParams& fp, cudaStream_t st) {
+    if (a.B == 0) return LDPCB_OK;
+    const int smem = (int)sizeof(OsdSmem);
+    static thread_local int occ_cache[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int& occ = occ_cache[h->device & 7];
+    if (occ == 0) {
+        LDPCB_CUDA(h, cudaFuncSetAttribute(osd_fs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        LDPCB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, osd_fs_kernel, OSD_THREADS, smem));
+        if (occ < 1) occ = 1;
+    }
+    int64_t want = (a.B + OSD_FPB - 1) / OSD_FPB;
+    int64_t cap = (int64_t)h->sm_count * occ;
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    osd_fs_kernel<<<grid, OSD_THREADS, smem, st>>>(a, fp, h->gcol_dev);
+    LDPCB_LAUNCH_CHECK(h, "osd_fs_kernel");
+    return LDPCB_OK;
+}
+
 template <int MAXW, bool BLOCKS>
 static int launch_variant(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st) {
     auto kern = osd_kernel<MAXW, BLOCKS>;
@@ -536,4 +772,26 @@ extern "C" int ldpcb_osd_block_minima(ldpcb_t* h, const float* order_llr_dev, co
     a.block_min_q = block_min_q_dev; a.block_arg = block_arg_dev; a.score_exp = score_exp_dev;
     a.truth_bits = truth_bits_dev; a.truth_score_q = truth_score_q_dev; a.perm = perm_dev;
     return launch_osd(h, a, (cudaStream_t)stream);
+}
+
+extern "C" int ldpcb_osd_fs_decode(ldpcb_t* h, const float* llr_dev, int64_t B, int order_limit, float tau_e, int tau_psc,
+                                   float beta_shift, uint32_t* cw_bits_dev, int32_t* best_tep_dev, int32_t* num_teps_dev,
+                                   uint8_t* stop_kind_dev, int64_t* best_score_q_dev, int32_t* score_exp_dev,
+                                   uint8_t* perm_dev, void* stream) {
+    if (!h) return LDPCB_ERR_ARG;
+    if (B < 0 || order_limit < 0 || order_limit > 3)
+        return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_fs_decode: B=%lld order_limit=%d out of range", (long long)B, order_limit);
+    if (B == 0) return LDPCB_OK;
+    int st = check_llr(h, "ldpcb_osd_fs_decode", llr_dev, llr_dev);
+    if (st != LDPCB_OK) return st;
+    if (!cw_bits_dev) return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_fs_decode: NULL cw_bits");
+    const TepTable& t = h->tep[order_limit][LDPCB_TEP_FS];
+    OsdArgs a = {};
+    a.order_llr = llr_dev; a.score_llr = llr_dev; a.B = B; a.teps = t.dev; a.n_teps = t.n; a.maxw = t.maxw;
+    a.cw_bits = cw_bits_dev; a.best_tep = best_tep_dev; a.best_score_q = best_score_q_dev; a.score_exp = score_exp_dev;
+    a.perm = perm_dev;
+    FsParams fp;
+    fp.tau_e = tau_e; fp.tau_psc = tau_psc; fp.beta_shift = beta_shift; fp.order = order_limit;
+    fp.num_teps = num_teps_dev; fp.stop_kind = stop_kind_dev;
+    return launch_osd_fs(h, a, fp, (cudaStream_t)stream);
 }

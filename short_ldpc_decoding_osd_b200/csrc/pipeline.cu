@@ -247,6 +247,97 @@ extern "C" int ldpcb_osd_decode_host(ldpcb_t* h, const float* order_llr_host, co
     return sync_streams(h);
 }
 
+extern "C" int ldpcb_osd_sweep_host(ldpcb_t* h, const float* upd_order_llr_host, const float* upd_score_llr_host,
+                                    const uint64_t* redG_host, int64_t B, const uint32_t* teps_host, int32_t n_teps, int flags,
+                                    uint32_t* cw_bits_host, int32_t* best_tep_host, int64_t* best_score_q_host,
+                                    int32_t* score_exp_host) {
+    if (!h) return LDPCB_ERR_ARG;
+    if (B < 0 || n_teps < 1 || (flags & ~3)) return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_sweep_host: B=%lld n_teps=%d flags=%d out of range", (long long)B, n_teps, flags);
+    if (B == 0) return LDPCB_OK;
+    if (!upd_order_llr_host || !upd_score_llr_host || !redG_host || !teps_host || !cw_bits_host)
+        return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_sweep_host: NULL argument");
+    LDPCB_CUDA(h, cudaSetDevice(h->device));
+    const bool same = (upd_order_llr_host == upd_score_llr_host);
+    int maxw = 1;
+    for (int i = 0; i < n_teps; ++i) {
+        int w = 0;
+        for (int j = 0; j < 4; ++j) {
+            const unsigned t = (teps_host[i] >> (8 * j)) & 0xffu;
+            if (t < 64u) ++w; else if (t != 0xffu) return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_sweep_host: TEP %d has position %u", i, t);
+        }
+        maxw = std::max(maxw, w);
+    }
+    cudaStream_t st = h->streams[0];
+    Carver probe(nullptr);
+    probe.take<uint32_t>((size_t)n_teps);
+    const int64_t chunk = std::min<int64_t>(B, HOST_CHUNK);
+    probe.take<float>((size_t)chunk * N); probe.take<float>((size_t)chunk * N); probe.take<uint64_t>((size_t)chunk * K);
+    probe.take<uint32_t>((size_t)chunk * 4); probe.take<int32_t>((size_t)chunk); probe.take<int64_t>((size_t)chunk); probe.take<int32_t>((size_t)chunk);
+    int s = ensure_ws(h, 1, probe.off + 256);
+    if (s != LDPCB_OK) return s;
+    Carver c(h->ws[1].buf);
+    uint32_t* teps = c.take<uint32_t>((size_t)n_teps);
+    float* ol = c.take<float>((size_t)chunk * N);
+    float* sl = c.take<float>((size_t)chunk * N);
+    uint64_t* rg = c.take<uint64_t>((size_t)chunk * K);
+    uint32_t* bits = c.take<uint32_t>((size_t)chunk * 4);
+    int32_t* bt = c.take<int32_t>((size_t)chunk);
+    int64_t* bq = c.take<int64_t>((size_t)chunk);
+    int32_t* ex = c.take<int32_t>((size_t)chunk);
+    LDPCB_CUDA(h, cudaMemcpyAsync(teps, teps_host, sizeof(uint32_t) * n_teps, cudaMemcpyHostToDevice, st));
+    for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+        const int64_t nb = std::min(chunk, B - b0);
+        LDPCB_CUDA(h, cudaMemcpyAsync(ol, upd_order_llr_host + b0 * N, sizeof(float) * nb * N, cudaMemcpyHostToDevice, st));
+        if (!same) LDPCB_CUDA(h, cudaMemcpyAsync(sl, upd_score_llr_host + b0 * N, sizeof(float) * nb * N, cudaMemcpyHostToDevice, st));
+        LDPCB_CUDA(h, cudaMemcpyAsync(rg, redG_host + b0 * K, sizeof(uint64_t) * nb * K, cudaMemcpyHostToDevice, st));
+        OsdArgs a = {};
+        a.order_llr = ol; a.score_llr = same ? ol : sl; a.redG_in = rg; a.B = nb; a.teps = teps; a.n_teps = n_teps; a.maxw = maxw; a.flags = flags;
+        a.cw_bits = bits; a.best_tep = bt; a.best_score_q = bq; a.score_exp = ex;
+        if ((s = launch_osd(h, a, st)) != LDPCB_OK) return s;
+        LDPCB_CUDA(h, cudaMemcpyAsync(cw_bits_host + b0 * 4, bits, sizeof(uint32_t) * nb * 4, cudaMemcpyDeviceToHost, st));
+        if (best_tep_host) LDPCB_CUDA(h, cudaMemcpyAsync(best_tep_host + b0, bt, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, st));
+        if (best_score_q_host) LDPCB_CUDA(h, cudaMemcpyAsync(best_score_q_host + b0, bq, sizeof(int64_t) * nb, cudaMemcpyDeviceToHost, st));
+        if (score_exp_host) LDPCB_CUDA(h, cudaMemcpyAsync(score_exp_host + b0, ex, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, st));
+        LDPCB_CUDA(h, cudaStreamSynchronize(st));
+    }
+    return LDPCB_OK;
+}
+
+extern "C" int ldpcb_osd_fs_decode_host(ldpcb_t* h, const float* llr_host, int64_t B, int order_limit, float tau_e, int tau_psc,
+                                        float beta_shift, uint32_t* cw_bits_host, int32_t* best_tep_host,
+                                        int32_t* num_teps_host, uint8_t* stop_kind_host) {
+    if (!h) return LDPCB_ERR_ARG;
+    if (B < 0 || order_limit < 0 || order_limit > 3) return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_fs_decode_host: bad arguments");
+    if (B == 0) return LDPCB_OK;
+    if (!llr_host || !cw_bits_host) return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_fs_decode_host: NULL llr or cw_bits");
+    LDPCB_CUDA(h, cudaSetDevice(h->device));
+    int ci = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += HOST_CHUNK, ++ci) {
+        const int64_t nb = std::min(HOST_CHUNK, B - b0);
+        const int slot = 1 + ci % 3;
+        cudaStream_t st = h->streams[ci % 3];
+        Carver probe(nullptr);
+        probe.take<float>((size_t)nb * N); probe.take<uint32_t>((size_t)nb * 4); probe.take<int32_t>((size_t)nb);
+        probe.take<int32_t>((size_t)nb); probe.take<uint8_t>((size_t)nb);
+        int s = ensure_ws(h, slot, probe.off + 256);
+        if (s != LDPCB_OK) return s;
+        Carver c(h->ws[slot].buf);
+        float* llr = c.take<float>((size_t)nb * N);
+        uint32_t* bits = c.take<uint32_t>((size_t)nb * 4);
+        int32_t* bt = c.take<int32_t>((size_t)nb);
+        int32_t* nt = c.take<int32_t>((size_t)nb);
+        uint8_t* sk = c.take<uint8_t>((size_t)nb);
+        LDPCB_CUDA(h, cudaMemcpyAsync(llr, llr_host + b0 * N, sizeof(float) * nb * N, cudaMemcpyHostToDevice, st));
+        s = ldpcb_osd_fs_decode(h, llr, nb, order_limit, tau_e, tau_psc, beta_shift, bits, bt, nt, sk, nullptr, nullptr, nullptr, st);
+        if (s != LDPCB_OK) return s;
+        LDPCB_CUDA(h, cudaMemcpyAsync(cw_bits_host + b0 * 4, bits, sizeof(uint32_t) * nb * 4, cudaMemcpyDeviceToHost, st));
+        if (best_tep_host) LDPCB_CUDA(h, cudaMemcpyAsync(best_tep_host + b0, bt, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, st));
+        if (num_teps_host) LDPCB_CUDA(h, cudaMemcpyAsync(num_teps_host + b0, nt, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, st));
+        if (stop_kind_host) LDPCB_CUDA(h, cudaMemcpyAsync(stop_kind_host + b0, sk, (size_t)nb, cudaMemcpyDeviceToHost, st));
+    }
+    return sync_streams(h);
+}
+
 extern "C" int ldpcb_decode_host(ldpcb_t* h, const float* llr_host, int64_t B, int iters, float alpha_check, float w_vc,
                                  float w_marg, int early_stop, int osd_order, int tep_order,
                                  uint32_t* final_bits_host, uint8_t* syndrome_nz_host, int32_t* best_tep_host,
