@@ -114,11 +114,14 @@ __device__ __forceinline__ unsigned transpose32(unsigned x, int lane) {
 
 // ---- 1. sort: descending key, payload = original index; lane holds sorted positions 4*lane + k ------
 __device__ __forceinline__ void ce_lane(unsigned& ka, unsigned& ia, unsigned& kb, unsigned& ib, bool asc) {
-    const bool sw = asc ? (ka > kb) : (ka < kb);
-    if (sw) {
-        unsigned t = ka; ka = kb; kb = t;
-        t = ia; ia = ib; ib = t;
-    }
+    const unsigned mn = min(ka, kb), mx = max(ka, kb);
+    const unsigned na = asc ? mn : mx, nb = asc ? mx : mn;
+    const bool sw = (na != ka);  // equal keys never swap
+    const unsigned ta = ia;
+    ia = sw ? ib : ia;
+    ib = sw ? ta : ib;
+    ka = na;
+    kb = nb;
 }
 
 __device__ __forceinline__ void bitonic_sort_desc(unsigned (&key)[4], unsigned (&idx)[4], int lane) {
@@ -135,8 +138,9 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned (&key)[4], unsigned (
                 for (int k = 0; k < 4; ++k) {
                     const unsigned ok = __shfl_xor_sync(0xffffffffu, key[k], lm);
                     const unsigned oi = __shfl_xor_sync(0xffffffffu, idx[k], lm);
-                    const bool take = keep_min ? (ok < key[k]) : (ok > key[k]);  // strict: ties stay put on both sides
-                    if (take) { key[k] = ok; idx[k] = oi; }
+                    const unsigned nk = keep_min ? min(key[k], ok) : max(key[k], ok);
+                    idx[k] = (nk != key[k]) ? oi : idx[k];  // equal keys stay put on both sides
+                    key[k] = nk;
                 }
             } else {
                 // element index i = 4*lane + k
@@ -218,43 +222,61 @@ __device__ __forceinline__ Prep prepare_frame(const OsdArgs& a, FrameSm& F, cons
             reinterpret_cast<unsigned*>(F.pi1)[lane] = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
         }
         // ---- 2. GF(2) elimination, column-major ----------------------------------------------
-        unsigned long long col[4];
+        unsigned clo[4], chi[4];  // columns as two 32-bit halves: every step works on one half with 32-bit ops
 #pragma unroll
-        for (int k = 0; k < 4; ++k) col[k] = gcol[idx[k]];
+        for (int k = 0; k < 4; ++k) {
+            const unsigned long long g = gcol[idx[k]];
+            clo[k] = (unsigned)g;
+            chi[k] = (unsigned)(g >> 32);
+        }
         {
-            unsigned long long used = 0ull;
-            int npiv = 0, nlrb = 0;
-            for (int l = 0; l < 32; ++l) {
+            unsigned used_lo = 0u, used_hi = 0u;
+            int npiv = 0, nlrb = 0, c_next = N;
+            for (int l = 0; l < 32 && npiv < K; ++l) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const int c = 4 * l + k;
-                    if (npiv == K) {  // basis complete: everything left is LRB
-                        if (lane == 0) F.pos[K + nlrb] = (unsigned char)c;
-                        ++nlrb;
-                        continue;
-                    }
-                    const unsigned long long cc = shfl64(col[k], l);
-                    const unsigned long long cand = cc & ~used;
-                    if (cand == 0ull) {  // dependent on more reliable columns
-                        if (lane == 0) F.pos[K + nlrb] = (unsigned char)c;
-                        ++nlrb;
-                        continue;
-                    }
-                    const int p = __ffsll((long long)cand) - 1;
-                    used |= 1ull << p;
-                    if (lane == 0) { F.pos[npiv] = (unsigned char)c; F.prow_of[npiv] = (unsigned char)p; }
-                    ++npiv;
-                    const unsigned long long m = cc ^ (1ull << p);
-                    if (m != 0ull) {  // an untouched unit column (an information position of G) needs no row operation
+                    if (npiv < K) {
+                        const int c = 4 * l + k;
+                        const unsigned cl = __shfl_sync(0xffffffffu, clo[k], l);
+                        const unsigned ch = __shfl_sync(0xffffffffu, chi[k], l);
+                        const unsigned al = cl & ~used_lo, ah = ch & ~used_hi;
+                        if ((al | ah) == 0u) {  // dependent on more reliable columns
+                            if (lane == 0) F.pos[K + nlrb] = (unsigned char)c;
+                            ++nlrb;
+                        } else {
+                            int p;
+                            if (al != 0u) {  // pivot row in the low word (any unused row with a 1 gives the same basis)
+                                const unsigned bit = al & (0u - al);
+                                p = 31 - __clz(bit);
+                                used_lo |= bit;
+                                const unsigned ml = cl ^ bit;
+                                if ((ml | ch) != 0u) {  // an untouched unit column (information position of G) needs no row operation
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            if ((col[kk] >> p) & 1ull) col[kk] ^= m;
+                                    for (int kk = 0; kk < 4; ++kk)
+                                        if (clo[kk] & bit) { clo[kk] ^= ml; chi[kk] ^= ch; }
+                                }
+                            } else {
+                                const unsigned bit = ah & (0u - ah);
+                                p = 63 - __clz(bit);
+                                used_hi |= bit;
+                                const unsigned mh = ch ^ bit;
+                                if ((cl | mh) != 0u) {
+#pragma unroll
+                                    for (int kk = 0; kk < 4; ++kk)
+                                        if (chi[kk] & bit) { clo[kk] ^= cl; chi[kk] ^= mh; }
+                                }
+                            }
+                            if (lane == 0) { F.pos[npiv] = (unsigned char)c; F.prow_of[npiv] = (unsigned char)p; }
+                            if (++npiv == K) c_next = c + 1;
+                        }
                     }
                 }
             }
+            // basis complete: every remaining position is LRB
+            for (int t = lane; c_next + t < N; t += 32) F.pos[K + nlrb + t] = (unsigned char)(c_next + t);
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) cols[4 * lane + k] = col[k];
+        for (int k = 0; k < 4; ++k) cols[4 * lane + k] = ((unsigned long long)chi[k] << 32) | clo[k];
         __syncwarp();
         // ---- permutation pi2 o pi1 -----------------------------------------------------------
 #pragma unroll
