@@ -245,6 +245,14 @@ def run_ours(args):
     cwb = torch.empty((max(nfail, 1), 4), dtype=torch.int32, device=devs)
     osd_ms = timed(lambda: h.call("ldpcb_osd_decode", fl, fl, nfail, order, 0, 0, cwb, None, None, None, None, None, sp)) if nfail else 0.0
     peaks, peak_src = measured_peaks()
+    traffic = None
+    try:  # DRAM bytes per frame measured once under ncu (profiles/), scaled to the frames of this launch
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tj = json.load(f)
+        per_frame = tj["osd_kernel" if osd_ms >= nms_ms else "nms_kernel"]["dram_bytes_per_frame"]
+        traffic = per_frame * (nfail if osd_ms >= nms_ms else B)
+    except Exception:
+        traffic = None
     step_ms = total_ms / K
     dom_is_osd = osd_ms >= nms_ms
     dom_ms = osd_ms if dom_is_osd else nms_ms
@@ -253,7 +261,8 @@ def run_ours(args):
     roofline = {
         "bound": "hbm", "kernel": "osd_kernel<2,false>" if dom_is_osd else "nms_kernel<5,3,false,false>",
         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-        "traffic": None, "peak_source": peak_src, "kernel_ms": dom_ms, "share_of_step": dom_ms / step_ms,
+        "traffic": traffic, "traffic_source": "profiles/r01_traffic.json (ncu dram__bytes per frame x frames of this launch)" if traffic else None,
+        "peak_source": peak_src, "kernel_ms": dom_ms, "share_of_step": dom_ms / step_ms,
         "algorithmic_bytes_per_launch": dom_bytes,
         "note": "both kernels are integer/FP32 issue-bound, not HBM-bound (SURVEY.md 8d): the HBM fraction is reported as BASELINE asks; "
                 "the binding resource is SM issue slots -- see profiles/ for sm__inst_executed / issue-active from ncu",

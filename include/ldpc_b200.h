@@ -237,6 +237,22 @@ int ldpcb_osd_fs_decode_host(ldpcb_t* h, const float* llr_host, int64_t B, int o
                              float beta_shift, uint32_t* cw_bits_host, int32_t* best_tep_host, int32_t* num_teps_host,
                              uint8_t* stop_kind_host);
 
+/*
+ * PB-OSD (probability-based OSD) policy.  Replaces the per-frame body of pb_osd(snr, selected_ds)
+ * (PB_OSD/pb_testing.py:100-149): best-first TEP order (optimal_tep_sequence, :366-397), promising-probability
+ * stop (:128-132, :399-447) and success-probability stop (:137-149, :410-423) with the thresholds of
+ * calculate_two_thresholds (:485-500).  order_limit 0..2.
+ *   llr_dev [B,128] channel LLR of the frames; snr_db the Eb/N0 the reference passes as `snr` (:50-52)
+ *   cw_bits_dev [B,4] out: optimal_codeword, original bit positions
+ *   stats_dev [B,4] int32 out (may be NULL): TEPs visited (cost_tep_num or N_max), p_e^pro passes
+ *   (counter_suc_sum1), improvements (counter_suc_sum2), list comparisons (memory_sum)
+ */
+int ldpcb_osd_pb_decode(ldpcb_t* h, const float* llr_dev, int64_t B, int order_limit, float snr_db,
+                        uint32_t* cw_bits_dev, int32_t* stats_dev, int64_t* best_score_q_dev,
+                        int32_t* score_exp_dev, void* stream);
+int ldpcb_osd_pb_decode_host(ldpcb_t* h, const float* llr_host, int64_t B, int order_limit, float snr_db,
+                             uint32_t* cw_bits_host, int32_t* stats_host);
+
 /* Number of TEPs of an enumeration (1, 65, 2081, 43745 for order 0..3), or a negative status. */
 int ldpcb_tep_count(ldpcb_t* h, int order, int tep_order);
 /* Copy the enumeration to the host in the packed format described above (n = ldpcb_tep_count). */

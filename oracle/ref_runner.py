@@ -4,7 +4,7 @@ tests/golden/*.npz.  /root/reference only exists in the build container, so the 
 and the tests read the fixtures.
 
     python oracle/ref_runner.py all          # regenerate every fixture (a few minutes)
-    python oracle/ref_runner.py nms|osd|fs|dl|gf2|gen
+    python oracle/ref_runner.py nms|osd|fs|pb|dl|gf2|gen
 
 Each sub-command runs in its own process with sys.path = [oracle/tf_shim, <one reference directory>]
 because the reference's directories all define modules with the same names (globalmap, fill_matrix_info,
@@ -211,6 +211,57 @@ def run_fs():
     np.savez_compressed(os.path.join(GOLD, "fs_ref_shim.npz"), y=y, labels=lab.astype(np.uint8), beta=0.1, tau_psc=30, d_min=14, **res)
 
 
+def run_pb():
+    """PB_OSD: per-frame outcome of pb_osd (S/F, TEPs visited, improvement counters) parsed from its own log."""
+    _enter("PB_OSD")
+    import fill_matrix_info as F
+    import globalmap as GL
+
+    with _quiet():
+        code = F.Code(os.path.join(REF, "PB_OSD", ALIST))
+    GL.set_map("code_parameters", code)
+    GL.set_map("termination_num_threshlod", 100)
+    GL.set_map("convention_osd", False)
+    GL.set_map("miracle_view", False)
+    GL.set_map("pb_osd", True)
+    import pb_testing as R
+
+    class DS:
+        def __init__(self, y, lab):
+            self.b = [(y[None, :], lab[None, :])]
+
+        def as_numpy_iterator(self):
+            return iter(self.b)
+
+    y, lab = _failed(code, 36, 5)
+    res = {}
+    for order, snr in ((1, 2.5), (2, 2.5), (2, 3.5)):
+        GL.set_map("order_limit", order)
+        S, NT, ML, A1, A2 = [], [], [], [], []
+        for i in range(len(y)):
+            log = f"./log/PB-OSD-order-{order}.txt"
+            if os.path.exists(log):
+                os.remove(log)
+            with _quiet():
+                R.pb_osd(snr, DS(y[i], lab[i]))
+            txt = open(log).read()
+            m = re.search(r"S/F:(\d+)/(\d+)", txt)
+            t = re.search(r"Average TEPs:([0-9.]+) Maintained_list_len:([0-9.]+) Average_suc: ([0-9.]+)/([0-9.]+)", txt)
+            S.append(int(m.group(1)))
+            NT.append(int(round(float(t.group(1)))))
+            ML.append(int(round(float(t.group(2)))))
+            A1.append(int(round(float(t.group(3)))))
+            A2.append(int(round(float(t.group(4)))))
+        tag = f"o{order}_snr{int(snr * 10)}"
+        res[f"success_{tag}"] = np.array(S)
+        res[f"num_teps_{tag}"] = np.array(NT)
+        res[f"list_cmp_{tag}"] = np.array(ML)
+        res[f"suc1_{tag}"] = np.array(A1)
+        res[f"suc2_{tag}"] = np.array(A2)
+        print(tag, S, NT, flush=True)
+    np.savez_compressed(os.path.join(GOLD, "pb_ref_shim.npz"), y=y, labels=lab.astype(np.uint8), **res)
+
+
 def run_dl():
     """DL_OSD_Testing_serial: H-based ordering, TEP blocks, sliding_osd with a fixed window classifier."""
     _enter("DL_OSD_Testing_serial")
@@ -320,13 +371,13 @@ def run_gf2():
                         n_swaps=np.array(nsw))
 
 
-CMDS = {"gen": run_gen, "nms": run_nms, "osd": run_osd, "fs": run_fs, "dl": run_dl, "gf2": run_gf2}
+CMDS = {"gen": run_gen, "nms": run_nms, "osd": run_osd, "fs": run_fs, "pb": run_pb, "dl": run_dl, "gf2": run_gf2}
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     os.makedirs(GOLD, exist_ok=True)
     if which == "all":
-        for name in ("gen", "gf2", "nms", "osd", "fs", "dl"):
+        for name in ("gen", "gf2", "nms", "osd", "fs", "pb", "dl"):
             print("==", name, flush=True)
             subprocess.run([sys.executable, os.path.abspath(__file__), name], check=True)
     else:

@@ -51,6 +51,8 @@ SYMBOLS = {
     "ldpcb_osd_sweep_host": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "ldpcb_osd_fs_decode": (_i32, [_vp, _vp, _i64, _i32, _f32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ldpcb_osd_fs_decode_host": (_i32, [_vp, _vp, _i64, _i32, _f32, _i32, _f32, _vp, _vp, _vp, _vp]),
+    "ldpcb_osd_pb_decode": (_i32, [_vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
+    "ldpcb_osd_pb_decode_host": (_i32, [_vp, _vp, _i64, _i32, _f32, _vp, _vp]),
     "ldpcb_decode_host": (_i32, [_vp, _vp, _i64, _i32, _f32, _f32, _f32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "ldpcb_host_alloc": (_i32, [C.POINTER(_vp), _u64]),
     "ldpcb_host_free": (_i32, [_vp]),

@@ -146,6 +146,15 @@ struct FsParams {
 };
 int launch_osd_fs(ldpcb_handle* h, const OsdArgs& a, const FsParams& fp, cudaStream_t st);
 
+// PB-OSD policy parameters (PB_OSD/pb_testing.py:44-52,100-149)
+struct PbParams {
+    float c4;             // -4 * noise_variance, noise_variance = 10^(-snr/10) (pb_testing.py:51-52)
+    int order;            // order_limit (0..2)
+    int32_t* stats;       // [B,4] out: TEPs visited, p_e^pro passes, improvements, list comparisons
+    double cdf_half[65];  // BinCDF(b; 64, 1/2)
+};
+int launch_osd_pb(ldpcb_handle* h, const OsdArgs& a, const PbParams& pp, cudaStream_t st);
+
 int build_tep_tables(ldpcb_handle* h);
 
 }  // namespace ldpcb

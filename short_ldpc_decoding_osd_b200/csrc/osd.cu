@@ -27,340 +27,9 @@
 //      score = base + sum delta_t + sum_b LUT_b[byte_b(D)]
 //   6. lexicographic (score, index) minimum = first minimum in enumeration order (tf.argmin)
 #include "common.cuh"
+#include "osd_prepare.cuh"
 
 namespace ldpcb {
-
-constexpr int OSD_FPB = 4;  // frames (= warps) per CTA
-constexpr int OSD_THREADS = OSD_FPB * 32;
-
-struct __align__(16) FrameSm {
-    unsigned long long prow[66];  // P' rows by MRB position, [64] = 0 for padded TEP slots
-    long long qd[66];             // signed score delta of flipping MRB position t, [64] = 0
-    unsigned long long qlrb[64];  // q of the LRB positions          (qd..qlrb are reused as cols[128])
-    float yo[N];                  // ordering metric (original positions)
-    float ys[N];                  // scoring metric
-    unsigned long long d0;        // order-0 discrepancy on the LRB
-    long long base;               // order-0 discrepancy weight on the MRB
-    unsigned long long d0m;       // order-0 discrepancy bits on the MRB (0 when both metrics agree)
-    unsigned char pi1[N];         // sorted position -> original index
-    unsigned char pos[N];         // permuted position (MRB then LRB) -> sorted position
-    unsigned char prow_of[K];     // pivot row of MRB position t
-    unsigned char tmp[N];
-};
-
-struct __align__(16) OsdSmem {
-    unsigned long long lut[8][256];  // 16 KB, shared by the four frames in turn
-    FrameSm fr[OSD_FPB];
-    long long red_s[OSD_FPB][OSD_FPB];  // [frame][warp] partial minima
-    int red_i[OSD_FPB][OSD_FPB];
-    int red_stop[OSD_FPB];           // FS: per-warp first stopping TEP index
-    long long fs_score[OSD_FPB];     // FS results per frame
-    int fs_opt[OSD_FPB], fs_num[OSD_FPB], fs_kind[OSD_FPB];
-};
-
-__device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) {
-    unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src);
-    unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
-    return ((unsigned long long)hi << 32) | lo;
-}
-__device__ __forceinline__ unsigned long long shfl_xor64(unsigned long long v, int m) {
-    unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, m);
-    unsigned hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), m);
-    return ((unsigned long long)hi << 32) | lo;
-}
-__device__ __forceinline__ long long warp_sum_ll(long long v) {
-#pragma unroll
-    for (int m = 16; m; m >>= 1) v += (long long)shfl_xor64((unsigned long long)v, m);
-    return v;
-}
-__device__ __forceinline__ unsigned long long warp_xor_ull(unsigned long long v) {
-#pragma unroll
-    for (int m = 16; m; m >>= 1) v ^= shfl_xor64(v, m);
-    return v;
-}
-__device__ __forceinline__ void warp_argmin(long long& s, int& i) {
-#pragma unroll
-    for (int m = 16; m; m >>= 1) {
-        const long long os = (long long)shfl_xor64((unsigned long long)s, m);
-        const int oi = __shfl_xor_sync(0xffffffffu, i, m);
-        if (os < s || (os == s && oi < i)) { s = os; i = oi; }
-    }
-}
-
-// exact integer reliability: q = rint(a * 2^(54-E)); a finite >= 0, E = frexp exponent of the frame max
-__device__ __forceinline__ long long quantize(float a, int E) {
-    const double scale = __hiloint2double((1023 + 54 - E) << 20, 0);
-    return __double2ll_rn((double)a * scale);
-}
-
-// |y| used for scoring: NaN -> 0, inf -> FLT_MAX
-__device__ __forceinline__ float score_abs(float y) {
-    float a = fabsf(y);
-    if (!(a == a)) a = 0.0f;
-    return fminf(a, 3.402823466e38f);
-}
-
-// 32x32 bit-matrix transpose across the warp: in: lane i holds word x_i; out: bit j of lane i = bit i of x_j
-__device__ __forceinline__ unsigned transpose32(unsigned x, int lane) {
-    unsigned m = 0x0000ffffu;
-#pragma unroll
-    for (int j = 16; j; j >>= 1) {
-        const unsigned y = __shfl_xor_sync(0xffffffffu, x, j);
-        x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y & m) << j));
-        m ^= m << (j >> 1);
-    }
-    return x;
-}
-
-// ---- 1. sort: descending key, payload = original index; lane holds sorted positions 4*lane + k ------
-__device__ __forceinline__ void ce_lane(unsigned& ka, unsigned& ia, unsigned& kb, unsigned& ib, bool asc) {
-    const unsigned mn = min(ka, kb), mx = max(ka, kb);
-    const unsigned na = asc ? mn : mx, nb = asc ? mx : mn;
-    const bool sw = (na != ka);  // equal keys never swap
-    const unsigned ta = ia;
-    ia = sw ? ib : ia;
-    ib = sw ? ta : ib;
-    ka = na;
-    kb = nb;
-}
-
-__device__ __forceinline__ void bitonic_sort_desc(unsigned (&key)[4], unsigned (&idx)[4], int lane) {
-#pragma unroll
-    for (int kk = 2; kk <= N; kk <<= 1) {
-#pragma unroll
-        for (int j = kk >> 1; j > 0; j >>= 1) {
-            if (j >= 4) {
-                const int lm = j >> 2;
-                const bool lower = (lane & lm) == 0;
-                const bool asc = (kk < N) && ((lane & (kk >> 2)) != 0);  // final merge is descending
-                const bool keep_min = (lower == asc);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const unsigned ok = __shfl_xor_sync(0xffffffffu, key[k], lm);
-                    const unsigned oi = __shfl_xor_sync(0xffffffffu, idx[k], lm);
-                    const unsigned nk = keep_min ? min(key[k], ok) : max(key[k], ok);
-                    idx[k] = (nk != key[k]) ? oi : idx[k];  // equal keys stay put on both sides
-                    key[k] = nk;
-                }
-            } else {
-                // element index i = 4*lane + k
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if ((k & j) == 0) {
-                        const int i_bit = (kk == 2) ? (k & 2) : (kk == 4 ? (lane & 1) : (lane & (kk >> 2)));
-                        const bool asc = (kk < N) && (i_bit != 0);
-                        ce_lane(key[k], idx[k], key[k | j], idx[k | j], asc);
-                    }
-                }
-            }
-        }
-    }
-}
-
-// Registers a warp keeps about its frame between prepare and output.
-struct Prep {
-    unsigned char pm[4];            // original index of permuted positions lane, lane+32 (MRB), lane+64, lane+96 (LRB)
-    unsigned long long myprow[2];   // P' rows of MRB positions lane, lane+32
-    unsigned long long hd_lrb;      // hard decisions the discrepancy is measured against, LRB part
-    unsigned long long hd_mrb;      // same, MRB part
-    unsigned long long ho_mrb;      // MRB hard decisions of the ordering metric (order-0 information bits)
-    unsigned long long d0;          // order-0 discrepancy on the LRB
-    int E;                          // score exponent
-};
-
-// Steps 1-4 for one frame by one warp; fills F (prow, qd, qlrb, d0, base) and returns the registers above.
-template <bool TRUTH>
-__device__ __forceinline__ Prep prepare_frame(const OsdArgs& a, FrameSm& F, const uint64_t* __restrict__ gcol, int64_t row,
-                                              int64_t f, int lane, bool ties_high, bool disc_from_score) {
-    unsigned long long* cols = reinterpret_cast<unsigned long long*>(F.qd);  // [128], dead before qd/qlrb are written
-    unsigned char pm[4] = {0, 0, 0, 0};
-    unsigned long long myprow[2] = {0ull, 0ull};
-    unsigned long long hd_lrb = 0ull, ho_mrb = 0ull, d0 = 0ull;
-    int E = 0;
-    // ---- load ---------------------------------------------------------------------------
-    const float4 v = reinterpret_cast<const float4*>(a.order_llr + row * N)[lane];
-    reinterpret_cast<float4*>(F.yo)[lane] = v;
-    reinterpret_cast<float4*>(F.ys)[lane] = reinterpret_cast<const float4*>(a.score_llr + row * N)[lane];
-    if (a.redG_in) {
-        // pre-permuted frame with its systematic generator rows (convention_osd_main's inputs)
-        myprow[0] = a.redG_in[row * K + lane];
-        myprow[1] = a.redG_in[row * K + lane + 32];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) pm[k] = (unsigned char)(lane + 32 * k);
-        __syncwarp();
-    } else {
-        // ---- 1. sort --------------------------------------------------------------------
-        unsigned key[4] = {__float_as_uint(v.x) & 0x7fffffffu, __float_as_uint(v.y) & 0x7fffffffu,
-                           __float_as_uint(v.z) & 0x7fffffffu, __float_as_uint(v.w) & 0x7fffffffu};
-        unsigned idx[4] = {4u * lane, 4u * lane + 1, 4u * lane + 2, 4u * lane + 3};
-        bitonic_sort_desc(key, idx, lane);
-        const unsigned nxt = __shfl_down_sync(0xffffffffu, key[0], 1);
-        const bool tie = (key[0] == key[1]) || (key[1] == key[2]) || (key[2] == key[3]) || (lane < 31 && key[3] == nxt);
-        if (__any_sync(0xffffffffu, tie)) {
-            // exact rank sort with the tf.argsort tie rule (stable: lower index first; reversed-ascending: higher first)
-            __syncwarp();
-            unsigned mykey[4];
-            int rank[4] = {0, 0, 0, 0};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) mykey[k] = __float_as_uint(F.yo[4 * lane + k]) & 0x7fffffffu;
-            for (int i = 0; i < N; ++i) {
-                const unsigned ki = __float_as_uint(F.yo[i]) & 0x7fffffffu;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int j = 4 * lane + k;
-                    const bool first = ties_high ? (i > j) : (i < j);
-                    rank[k] += (ki > mykey[k]) || (ki == mykey[k] && first);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) F.pi1[rank[k]] = (unsigned char)(4 * lane + k);
-            __syncwarp();
-            const unsigned w = reinterpret_cast<const unsigned*>(F.pi1)[lane];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) idx[k] = (w >> (8 * k)) & 0xffu;
-        } else {
-            reinterpret_cast<unsigned*>(F.pi1)[lane] = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
-        }
-        // ---- 2. GF(2) elimination, column-major ----------------------------------------------
-        unsigned clo[4], chi[4];  // columns as two 32-bit halves: every step works on one half with 32-bit ops
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const unsigned long long g = gcol[idx[k]];
-            clo[k] = (unsigned)g;
-            chi[k] = (unsigned)(g >> 32);
-        }
-        {
-            unsigned used_lo = 0u, used_hi = 0u;
-            int npiv = 0, nlrb = 0, c_next = N;
-            for (int l = 0; l < 32 && npiv < K; ++l) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (npiv < K) {
-                        const int c = 4 * l + k;
-                        const unsigned cl = __shfl_sync(0xffffffffu, clo[k], l);
-                        const unsigned ch = __shfl_sync(0xffffffffu, chi[k], l);
-                        const unsigned al = cl & ~used_lo, ah = ch & ~used_hi;
-                        if ((al | ah) == 0u) {  // dependent on more reliable columns
-                            if (lane == 0) F.pos[K + nlrb] = (unsigned char)c;
-                            ++nlrb;
-                        } else {
-                            int p;
-                            if (al != 0u) {  // pivot row in the low word (any unused row with a 1 gives the same basis)
-                                const unsigned bit = al & (0u - al);
-                                p = 31 - __clz(bit);
-                                used_lo |= bit;
-                                const unsigned ml = cl ^ bit;
-                                if ((ml | ch) != 0u) {  // an untouched unit column (information position of G) needs no row operation
-#pragma unroll
-                                    for (int kk = 0; kk < 4; ++kk)
-                                        if (clo[kk] & bit) { clo[kk] ^= ml; chi[kk] ^= ch; }
-                                }
-                            } else {
-                                const unsigned bit = ah & (0u - ah);
-                                p = 63 - __clz(bit);
-                                used_hi |= bit;
-                                const unsigned mh = ch ^ bit;
-                                if ((cl | mh) != 0u) {
-#pragma unroll
-                                    for (int kk = 0; kk < 4; ++kk)
-                                        if (chi[kk] & bit) { clo[kk] ^= cl; chi[kk] ^= mh; }
-                                }
-                            }
-                            if (lane == 0) { F.pos[npiv] = (unsigned char)c; F.prow_of[npiv] = (unsigned char)p; }
-                            if (++npiv == K) c_next = c + 1;
-                        }
-                    }
-                }
-            }
-            // basis complete: every remaining position is LRB
-            for (int t = lane; c_next + t < N; t += 32) F.pos[K + nlrb + t] = (unsigned char)(c_next + t);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) cols[4 * lane + k] = ((unsigned long long)chi[k] << 32) | clo[k];
-        __syncwarp();
-        // ---- permutation pi2 o pi1 -----------------------------------------------------------
-#pragma unroll
-        for (int k = 0; k < 4; ++k) pm[k] = F.pi1[F.pos[lane + 32 * k]];
-        // ---- 3. P' rows: 64x64 bit transpose of the LRB columns -------------------------------
-        const unsigned long long ca = cols[F.pos[K + lane]];
-        const unsigned long long cb = cols[F.pos[K + 32 + lane]];
-        const unsigned tA = transpose32((unsigned)ca, lane);          // rows 0..31,  LRB cols 0..31
-        const unsigned tB = transpose32((unsigned)(ca >> 32), lane);  // rows 32..63, LRB cols 0..31
-        const unsigned tC = transpose32((unsigned)cb, lane);          // rows 0..31,  LRB cols 32..63
-        const unsigned tD = transpose32((unsigned)(cb >> 32), lane);  // rows 32..63, LRB cols 32..63
-        __syncwarp();  // all reads of cols are done; reuse it for the physical rows
-        unsigned long long* rowsP = cols;  // rows in physical order, first 512 B of the free cols area
-        rowsP[lane] = ((unsigned long long)tC << 32) | tA;
-        rowsP[lane + 32] = ((unsigned long long)tD << 32) | tB;
-        __syncwarp();
-        myprow[0] = rowsP[F.prow_of[lane]];
-        myprow[1] = rowsP[F.prow_of[lane + 32]];
-        __syncwarp();  // rowsP dead before qd/qlrb are written below
-    }
-    // ---- 4. permuted metrics, exact reliabilities, order-0 codeword ----------------------------
-    float yo[4], ys[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { yo[k] = F.yo[pm[k]]; ys[k] = F.ys[pm[k]]; }
-    float as[4];
-    unsigned amax_bits = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        as[k] = score_abs(ys[k]);
-        amax_bits = max(amax_bits, __float_as_uint(as[k]));
-    }
-#pragma unroll
-    for (int m = 16; m; m >>= 1) amax_bits = max(amax_bits, __shfl_xor_sync(0xffffffffu, amax_bits, m));
-    frexpf(__uint_as_float(amax_bits), &E);
-    long long q[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) q[k] = quantize(as[k], E);
-    unsigned ho[4], hd[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        ho[k] = !(yo[k] > 0.0f);  // hard decision: 1 iff !(y > 0)   (convention_osd.py:54)
-        hd[k] = disc_from_score ? (unsigned)!(ys[k] > 0.0f) : ho[k];
-    }
-    long long base = 0;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const unsigned d0m = ho[k] ^ hd[k];
-        F.qd[lane + 32 * k] = d0m ? -q[k] : q[k];
-        base += d0m ? q[k] : 0ll;
-    }
-    base = warp_sum_ll(base);
-    F.qlrb[lane] = (unsigned long long)q[2];
-    F.qlrb[lane + 32] = (unsigned long long)q[3];
-    F.prow[lane] = myprow[0];
-    F.prow[lane + 32] = myprow[1];
-    unsigned long long c0 = (ho[0] ? myprow[0] : 0ull) ^ (ho[1] ? myprow[1] : 0ull);
-    c0 = warp_xor_ull(c0);
-    hd_lrb = (unsigned long long)__ballot_sync(0xffffffffu, hd[2]) | ((unsigned long long)__ballot_sync(0xffffffffu, hd[3]) << 32);
-    ho_mrb = (unsigned long long)__ballot_sync(0xffffffffu, ho[0]) | ((unsigned long long)__ballot_sync(0xffffffffu, ho[1]) << 32);
-    const unsigned long long hd_mrb_out = (unsigned long long)__ballot_sync(0xffffffffu, hd[0]) | ((unsigned long long)__ballot_sync(0xffffffffu, hd[1]) << 32);
-    d0 = c0 ^ hd_lrb;
-    if (lane == 0) { F.d0 = d0; F.base = base; F.d0m = ho_mrb ^ hd_mrb_out; F.prow[64] = 0ull; F.qd[64] = 0ll; }  // [64]: padded TEP slots (qd aliases cols until here)
-    if (TRUTH && a.truth_bits && a.truth_score_q) {
-        long long ts = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const unsigned tb = (a.truth_bits[row * 4 + (pm[k] >> 5)] >> (pm[k] & 31)) & 1u;
-            ts += (tb ^ hd[k]) ? q[k] : 0ll;
-        }
-        ts = warp_sum_ll(ts);
-        if (lane == 0) a.truth_score_q[f] = ts;
-    }
-    Prep r;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) r.pm[k] = pm[k];
-    r.myprow[0] = myprow[0];
-    r.myprow[1] = myprow[1];
-    r.hd_lrb = hd_lrb;
-    r.hd_mrb = hd_mrb_out;
-    r.ho_mrb = ho_mrb;
-    r.d0 = d0;
-    r.E = E;
-    return r;
-}
 
 template <int MAXW, bool BLOCKS>
 __global__ void __launch_bounds__(OSD_THREADS) osd_kernel(OsdArgs a, const uint64_t* __restrict__ gcol) {

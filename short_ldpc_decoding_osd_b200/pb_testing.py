@@ -8,11 +8,12 @@
   with the reference's pivot rule (the kernel does not call it; kept for API completeness and tests).
 * ``identify_mrb(order_inputs, order_G)`` -- pb_testing.py:268-304, host-side, built on ``full_gf2elim``.
 * ``miracle_view`` -- pb_testing.py:502-511, the genie statistic (MRB hard-decision errors per frame).
-* ``pb_osd(snr, selected_ds)`` -- pb_testing.py:44-229 driver: the ``convention_osd`` and ``miracle_view``
-  switches are served by the GPU sweep for all frames at once, with the reference's log lines.  The PB stopping
-  rule itself (best-first TEP order with the p_e^pro / p_e^suc tests, :100-149,366-500) is not implemented in
-  this round; with ``GL.pb_osd`` set the exhaustive order-p sweep is run instead and the
-  log says so -- its FER lower-bounds PB-OSD's, its TEP count upper-bounds it.
+* ``pb_osd(snr, selected_ds)`` -- pb_testing.py:44-229 driver.  With ``GL.pb_osd`` set the PB policy (best-first
+  TEP order, p_e^pro / p_e^suc stopping, :100-149,366-500) runs for all frames in one call of
+  ldpcb_osd_pb_decode_host (order_limit <= 2; order 3 would need a 43,745-entry list per frame and falls back
+  to the exhaustive sweep, logged as such); the ``convention_osd`` and ``miracle_view`` switches are served by
+  the exhaustive GPU sweep.  Same log lines as the reference.
+* ``pb_osd_batch(inputs, labels, snr, order_limit)`` -- the policy on [B,128] arrays.
 """
 from __future__ import annotations
 
@@ -92,6 +93,20 @@ def _frames_of(selected_ds):
     return np.asarray(ys, dtype=np.float32).reshape(-1, 128), np.asarray(labs).reshape(-1, 128)
 
 
+def pb_osd_batch(inputs, labels, snr, order_limit):
+    """PB-OSD on [B,128] channel LLRs -> dict(correct, num_teps, suc1, suc2, list_cmp, codeword)."""
+    y = np.ascontiguousarray(np.asarray(inputs, dtype=np.float32).reshape(-1, 128))
+    B = y.shape[0]
+    h = get_handle()
+    cw = np.empty((B, 4), np.uint32)
+    stats = np.empty((B, 4), np.int32)
+    h.call("ldpcb_osd_pb_decode_host", y, B, int(order_limit), float(snr), cw, stats)
+    codeword = _lib.unpack_bits(cw)
+    correct = (codeword == (np.asarray(labels).reshape(B, 128) & 1)).all(axis=1)
+    return {"correct": correct, "num_teps": stats[:, 0], "suc1": stats[:, 1], "suc2": stats[:, 2], "list_cmp": stats[:, 3],
+            "codeword": codeword}
+
+
 def pb_osd(snr, selected_ds):
     start_time = time.process_time()
     order_limit = GL.get_map("order_limit")
@@ -112,8 +127,32 @@ def pb_osd(snr, selected_ds):
             print(f"order-{key}: Accumulated Ratio: {acc/total:.4f}")
         summary["miracle"] = dict(counter_stat)
         return summary
-    res = cnv_OSD.convention_osd_batch(y, lab, order_limit)
     limit = GL.get_map("termination_num_threshlod") or 100
+    if GL.get_map("pb_osd") and not GL.get_map("convention_osd") and order_limit <= 2:
+        res = pb_osd_batch(y, lab, snr, order_limit)
+        fails_cum = np.cumsum(~res["correct"])
+        n_used = int(np.searchsorted(fails_cum, limit) + 1) if fails_cum.size and fails_cum[-1] >= limit else len(y)
+        ok = res["correct"][:n_used]
+        correct_sum, fail_sum = int(ok.sum()), int((~ok).sum())
+        actual = max(correct_sum + fail_sum, 1)
+        FER = round(fail_sum / actual, 4)
+        average_size = round(float(res["num_teps"][:n_used].sum()) / actual, 5)
+        average_num_memory = round(float(res["list_cmp"][:n_used].sum()) / actual, 5)
+        a1 = round(float(res["suc1"][:n_used].sum()) / actual, 5)
+        a2 = round(float(res["suc2"][:n_used].sum()) / actual, 5)
+        T2 = time.process_time()
+        log_filename = logdir + "PB-OSD-order-" + str(order_limit) + ".txt"
+        print("\nFor PB-OSD %.1fdB (order_limit:%d) :\n" % (snr, order_limit))
+        print("----> S:" + str(correct_sum) + " F:" + str(fail_sum) + "\n")
+        print(f"FER:{FER:.4f} Average TEPs:{average_size:.2f} Maintained_list_len:{average_num_memory:.2f} Average_suc: {a1:.2f}/{a2:.2f}")
+        with open(log_filename, "a+") as f:
+            f.write("\nFor PB-OSD %.1fdB (order_limit:%d) summary:\n" % (snr, order_limit))
+            f.write(f"--> S/F:{correct_sum}/{fail_sum}\n")
+            f.write(f"FER:{FER:.5f} Average TEPs:{average_size:.2f} Maintained_list_len:{average_num_memory:.2f} Average_suc: {a1:.2f}/{a2:2f}\n")
+            f.write(f"Running time:{T2 - start_time} seconds with mean time {(T2 - start_time)/actual:.4f}!\n")
+        summary.update({"S": correct_sum, "F": fail_sum, "FER": FER, "average_teps": average_size, "log": log_filename})
+        return summary
+    res = cnv_OSD.convention_osd_batch(y, lab, order_limit)
     # the reference stops after `limit` OSD failures (pb_testing.py:174, PB_OSD/globalmap.py:43)
     fails_cum = np.cumsum(~res["correct"])
     n_used = int(np.searchsorted(fails_cum, limit) + 1) if fails_cum.size and fails_cum[-1] >= limit else len(y)
@@ -122,7 +161,7 @@ def pb_osd(snr, selected_ds):
     counter = Counter(int(p) for p in res["phase"][:n_used])
     FER = round(F / max(S + F, 1), 4)
     T2 = time.process_time()
-    tag = "CNV-OSD" if GL.get_map("convention_osd") else "PB-OSD(exhaustive sweep, stopping rule not applied)"
+    tag = "CNV-OSD" if GL.get_map("convention_osd") else "PB-OSD(order 3: exhaustive sweep, stopping rule not applied)"
     log_filename = logdir + ("CNV-OSD-order-" if GL.get_map("convention_osd") else "PB-OSD-order-") + str(order_limit) + ".txt"
     print("\nFor %s %.1fdB (order_limit:%d) :\n" % (tag, snr, order_limit))
     print("----> S:" + str(S) + " F:" + str(F) + "\n")

@@ -1,0 +1,78 @@
+"""-m gpu: parity at scale against the C oracle (bit-identical to the NumPy oracle, see test_oracle_c.py),
+and FER against the reference points of tests/golden/fer_reference.json."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle as CO
+from oracle import osd_oracle as OO
+from oracle import philox_oracle as PO
+from short_ldpc_decoding_osd_b200 import _lib, simulate
+from tests.gpu_util import dev, empty, nms_gpu, osd_gpu, sync
+
+pytestmark = pytest.mark.gpu
+ALPHA = 0.66943514
+
+
+def test_nms_200k_frames_bit_exact(handle, code):
+    B = 200_000
+    y, cw, _ = PO.gen_frames(31337, 0, B, 2.5, code.G)
+    ref = CO.nms(y, code.H, 12, ALPHA)
+    got = nms_gpu(handle, y, 12, ALPHA, traj=False)
+    agree = (got["hard"] == ref["hard"]).all(axis=1).mean()
+    assert agree == 1.0  # bar: >= 99.99% of frames
+    assert np.array_equal(got["syndrome_nz"], ref["syndrome_nz"])
+    sub = slice(0, 20000)
+    ref_t = CO.nms(y[sub], code.H, 12, ALPHA, traj=True)["traj"]
+    got_t = nms_gpu(handle, y[sub], 12, ALPHA)["traj"]
+    np.testing.assert_allclose(got_t, ref_t, rtol=1e-5, atol=2e-6)
+    assert (got_t == ref_t).mean() > 0.9999  # in practice bit-identical
+    # early-stop variant too
+    ref_e = CO.nms(y[sub], code.H, 12, ALPHA, early_stop=True)
+    got_e = nms_gpu(handle, y[sub], 12, ALPHA, early=1, traj=False)
+    assert np.array_equal(got_e["hard"], ref_e["hard"]) and np.array_equal(got_e["iters_used"], ref_e["iters_used"])
+
+
+@pytest.mark.parametrize("order,n,tep_order,flags", [(1, 40000, 0, 0), (2, 20000, 0, 0), (2, 6000, 1, 1), (3, 600, 0, 0)])
+def test_osd_many_frames_bit_exact(handle, code, order, n, tep_order, flags):
+    y, cw, _ = PO.gen_frames(4242 + order, 0, 6 * n, 2.5, code.G)
+    syn = CO.nms(y, code.H, 12, ALPHA)["syndrome_nz"]
+    yf = np.ascontiguousarray(y[syn][:n])
+    teps = OO.pack_teps(OO.generate_teps_conv(order) if tep_order == 0 else OO.generate_teps_fs(order))
+    ref = CO.osd(yf, None, code.G, teps, flags=flags)
+    got = osd_gpu(handle, yf, order=order, tep_order=tep_order, flags=flags)
+    for k in ("perm", "best_tep", "best_score_q", "score_exp", "codeword", "redG"):
+        assert np.array_equal(got[k], ref[k]), k
+
+
+def test_osd_quantised_inputs_many_ties(handle, code):
+    """Every frame has many equal |y|: the exact tie path of the sort, at scale."""
+    y, cw, _ = PO.gen_frames(99, 0, 30000, 2.0, code.G)
+    yq = (np.round(y * 8) / 8).astype(np.float32)
+    teps = OO.pack_teps(OO.generate_teps_conv(1))
+    for flags in (0, 1):
+        ref = CO.osd(yq[:8000], None, code.G, teps, flags=flags)
+        got = osd_gpu(handle, yq[:8000], order=1, flags=flags)
+        for k in ("perm", "best_tep", "best_score_q", "codeword", "redG"):
+            assert np.array_equal(got[k], ref[k]), (flags, k)
+
+
+def test_fer_matches_reference_points(handle, golden_dir):
+    """FER of the GPU pipeline (Philox frames) against the reference generator + reference decoder points.
+    Two independent Monte-Carlo estimates: |difference| must stay below 3.5 combined standard errors, and the
+    inside-the-95%-CI flags are reported."""
+    ref = json.load(open(os.path.join(golden_dir, "fer_reference.json")))
+    inside = []
+    for i, pt in enumerate(ref["points"]):
+        for order in (1, 2):
+            n = 1 << 22
+            t = simulate.run_point(handle, pt["ebn0_db"], n, seed=500 + i, osd_order=order, chunk=1 << 21)
+            for ours, theirs, ci, k_ref in ((t.fer_nms, pt["fer_nms"], pt["fer_nms_ci95"], pt["frames"]),
+                                            (t.fer_final, pt[f"fer_final_osd{order}"], pt[f"fer_final_osd{order}_ci95"], pt["frames"])):
+                se = np.sqrt(ours * (1 - ours) / n + theirs * (1 - theirs) / k_ref)
+                assert abs(ours - theirs) <= 3.5 * se + 1e-12, (pt["ebn0_db"], order, ours, theirs, se)
+                inside.append(ci[0] <= ours <= ci[1])
+    assert np.mean(inside) >= 0.8  # a 95% interval of an independent estimate is missed ~5% of the time by chance
