@@ -157,6 +157,34 @@ class Decoding_model:
         return buffer_inputs, buffer_labels
 
 
+def save_decoded_data(updated_buffer, file_dir, snr, log_filename, list_length):
+    """ms_test.py:251-272: per-iteration mean cross-entropy of the failed frames appended to the log, and the
+    13-rows-per-failure retest file written as TFRecords (the input of PB_OSD / FS_OSD / DL_OSD_Testing_serial)."""
+    from . import read_TFdata
+
+    if len(updated_buffer[0]) == 0:
+        info = np.zeros((0, 128), np.float32)
+        label = np.zeros((0, 128), np.int64)
+    else:
+        info = np.stack([np.asarray(b, dtype=np.float32) for b in updated_buffer[0]])
+        label = np.stack([np.asarray(b) for b in updated_buffer[1]]).astype(np.int64)
+    CE_loss_list = []
+    n_cases = 0
+    for i in range(list_length):
+        bits, labs = info[i::list_length], label[i::list_length]
+        n_cases = bits.shape[0]
+        CE_loss_list.append(calculation_loss(bits, labs) / max(n_cases, 1))
+    print(CE_loss_list)
+    with open(log_filename, "a+") as f:
+        f.write(str(n_cases) + "tested:\n")
+        f.write("# CE list:\n")
+        f.write(" ".join(map(str, CE_loss_list)) + "\n")
+    print("Data for retraining  with %d cases to be stored " % info.shape[0])
+    read_TFdata.make_tfrecord((info, label), out_filename=file_dir)
+    print("For " + str(round(snr, 2)) + "dB:Data storing finished!")
+    return CE_loss_list
+
+
 def calculation_loss(soft_output, labels) -> float:
     """Sum of sigmoid cross-entropies with logits = -soft_output (ms_test.py:244-249); log-only statistic."""
     x = -np.asarray(soft_output, dtype=np.float64)

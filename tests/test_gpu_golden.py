@@ -211,3 +211,34 @@ def test_pb_policy_on_more_frames(handle, code):
         # probabilities are fp32 with expf/pow of two different libms: a stop decision may flip when a probability
         # sits within an ulp of its threshold
         assert mism <= 1, (order, snr, mism)
+
+
+def test_driver_chain_nms_to_retest_file_to_osd(handle, code, tmp_path, monkeypatch):
+    """The reference's file-coupled chain end to end with the drop-ins: ldpc_128_testing -> retest TFRecord
+    (13 rows per failure) -> fs_osd / pb_osd drivers reading it in batches of 13 (globalmap.data_setting)."""
+    from short_ldpc_decoding_osd_b200 import fs_testing, ldpc_128_testing, pb_testing, read_TFdata
+
+    monkeypatch.chdir(tmp_path)
+    argv = "python 2.5 2.5 1 500 4 12 CCSDS_ldpc_n128_k64.alist NMS-1".split()
+    fer_list = ldpc_128_testing.main(argv, data_root=str(tmp_path), frames_if_missing=2000)
+    assert len(fer_list) == 1 and 0.15 < fer_list[0][1] < 0.32
+    retest = tmp_path / "Testing_data_gen_128" / "data" / "snr2.5-2.5dB" / "NMS-1" / "12th" / "2.5dB" / "ldpc-nonzero-retest.tfrecord"
+    assert retest.exists()
+    ds = read_TFdata.data_handler(128, str(retest), 13)
+    batches = list(ds.as_numpy_iterator())
+    n_fail = len(batches)
+    assert all(b[0].shape == (13, 128) for b in batches) and abs(n_fail - fer_list[0][1] * 2000) <= 2
+    log = open(tmp_path / "log" / "FER-NMS-1-12th.txt").read()
+    assert "FER 0." in log and "CE list" in log
+    GL.set_map("order_limit", 1)
+    for k, v in dict(convention_osd=False, miracle_view=False, fs_osd=True, pb_osd=True, termination_num_threshlod=100000).items():
+        GL.set_map(k, v)
+    s_fs = fs_testing.fs_osd(2.5, 0.1, ds)
+    s_pb = pb_testing.pb_osd(2.5, ds)
+    GL.set_map("convention_osd", True)
+    s_cv = fs_testing.fs_osd(2.5, 0.1, ds)
+    GL.set_map("convention_osd", False)
+    assert s_fs["S"] + s_fs["F"] == s_pb["S"] + s_pb["F"] == s_cv["S"] + s_cv["F"] == n_fail
+    assert s_cv["F"] <= s_fs["F"] and s_cv["F"] <= s_pb["F"]  # the exhaustive sweep lower-bounds both policies
+    assert os.path.exists(s_fs["log"]) and os.path.exists(s_pb["log"])
+    GL.set_map("order_limit", 2)
