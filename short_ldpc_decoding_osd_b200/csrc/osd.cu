@@ -31,6 +31,42 @@
 
 namespace ldpcb {
 
+constexpr int OSD_WIN = 72;       // >= 64 LRB terms + 4 MRB terms + 1 base term
+constexpr int OSD_CAND_CAP = 32;
+
+// lut[b][x] = sum of q_lrb[8b+i] over the set bits i of x; thread: table b, low nibble fixed
+__device__ __forceinline__ void build_lut64(OsdSmem& S, const FrameSm& G, int tid) {
+    const int b = tid >> 4, lo = tid & 15;
+    unsigned long long wv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wv[i] = G.qlrb[8 * b + i];
+    unsigned long long lsum = 0ull;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) lsum += ((lo >> i) & 1) ? wv[i] : 0ull;
+    unsigned long long e[16];
+    e[0] = lsum;
+#pragma unroll
+    for (int x = 1; x < 16; ++x) e[x] = e[x & (x - 1)] + wv[4 + (31 - __clz(x & -x))];
+#pragma unroll
+    for (int x = 0; x < 16; ++x) S.lut[b][x * 16 + lo] = e[x];
+}
+
+// exact score of one TEP through the byte LUTs
+template <int MAXW>
+__device__ __forceinline__ long long score64(const OsdSmem& S, const FrameSm& G, unsigned tw) {
+    unsigned long long D = G.d0;
+    long long s = G.base;
+#pragma unroll
+    for (int j = 0; j < MAXW; ++j) {
+        const unsigned t = min((tw >> (8 * j)) & 0xffu, 64u);
+        D ^= G.prow[t];
+        s += G.qd[t];
+    }
+#pragma unroll
+    for (int b = 0; b < 8; ++b) s += (long long)S.lut[b][(unsigned)(D >> (8 * b)) & 0xffu];
+    return s;
+}
+
 template <int MAXW, bool BLOCKS>
 __global__ void __launch_bounds__(OSD_THREADS) osd_kernel(OsdArgs a, const uint64_t* __restrict__ gcol) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -53,50 +89,93 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_kernel(OsdArgs a, const uint6
         const unsigned long long* myprow = P.myprow;
         const unsigned long long hd_lrb = P.hd_lrb, ho_mrb = P.ho_mrb, d0 = P.d0;
         const int E = P.E;
-        // ---- 5./6. sweep: the four warps share one LUT and take the frames in turn ----------------------
+        // ---- 5./6. sweep: the four warps take the prepared frames in turn -------------------------------------
+        if (!BLOCKS && active && lane == 0) { S.cand_n[warp] = 0; S.cand_ovf[warp] = 0; }
         const int nfr = (int)((nframes - f0) < OSD_FPB ? (nframes - f0) : OSD_FPB);
         for (int w = 0; w < nfr; ++w) {
             const FrameSm& G = S.fr[w];
-            __syncthreads();  // frame w prepared; previous LUT no longer read
-            {
-                // lut[b][x] = sum of q_lrb[8b+i] over the set bits i of x; thread: table b, low nibble fixed
-                const int b = tid >> 4, lo = tid & 15;
-                unsigned long long wv[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) wv[i] = G.qlrb[8 * b + i];
-                unsigned long long lsum = 0ull;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) lsum += ((lo >> i) & 1) ? wv[i] : 0ull;
-                unsigned long long e[16];
-                e[0] = lsum;
-#pragma unroll
-                for (int x = 1; x < 16; ++x) e[x] = e[x & (x - 1)] + wv[4 + (31 - __clz(x & -x))];
-#pragma unroll
-                for (int x = 0; x < 16; ++x) S.lut[b][x * 16 + lo] = e[x];
-            }
-            __syncthreads();
-            const unsigned long long gd0 = G.d0;
-            const long long gbase = G.base;
+            __syncthreads();  // (A) frame w prepared; reduction slots and LUT free
             if (!BLOCKS) {
-                long long bs = 0x7fffffffffffffffll;
-                int bi = 0x7fffffff;
-                for (int i = tid; i < a.n_teps; i += OSD_THREADS) {
-                    const unsigned tw = __ldg(a.teps + i);
+                // Fast sweep on 32-bit truncated scores S32 = sum floor(term / 2^30): the 64 LRB weights are folded
+                // into thirteen 32-entry tables (5 bits of D each) that live in registers, one entry per lane, and
+                // are looked up with warp shuffles -- no shared-memory bank conflicts.  The exact score satisfies
+                // S32 * 2^30 <= S < (S32 + 69) * 2^30, so the exact first minimum is among the TEPs with
+                // S32 <= min S32 + OSD_WIN; those few are re-scored exactly at output.
+                int tabs[13];
+#pragma unroll
+                for (int j = 0; j < 13; ++j) {
+                    int v = 0;
+#pragma unroll
+                    for (int i = 0; i < 5; ++i)
+                        if (5 * j + i < 64) v += ((lane >> i) & 1) ? (int)G.w32[5 * j + i] : 0;
+                    tabs[j] = v;
+                }
+                const unsigned long long gd0 = G.d0;
+                const int gb32 = G.base32;
+                int s0 = 0x7fffffff, s1 = 0x7fffffff, s2 = 0x7fffffff, i0 = 0x7fffffff, i1 = 0x7fffffff, i2 = 0x7fffffff;
+                for (int ib = warp * 32; ib < a.n_teps; ib += OSD_THREADS) {
+                    const int i = ib + lane;
+                    const bool valid = i < a.n_teps;
+                    const unsigned tw = valid ? __ldg(a.teps + i) : 0xffffffffu;
                     unsigned long long D = gd0;
-                    long long s = gbase;
+                    int s = gb32;
 #pragma unroll
                     for (int j = 0; j < MAXW; ++j) {
                         const unsigned t = min((tw >> (8 * j)) & 0xffu, 64u);
                         D ^= G.prow[t];
-                        s += G.qd[t];
+                        s += G.qd32[t];
                     }
-#pragma unroll
-                    for (int b = 0; b < 8; ++b) s += (long long)S.lut[b][(unsigned)(D >> (8 * b)) & 0xffu];
-                    if (s < bs) { bs = s; bi = i; }
+                    const unsigned lo = (unsigned)D, hi = (unsigned)(D >> 32);
+                    s += __shfl_sync(0xffffffffu, tabs[0], lo);  // the source lane is taken modulo 32
+                    s += __shfl_sync(0xffffffffu, tabs[1], lo >> 5);
+                    s += __shfl_sync(0xffffffffu, tabs[2], lo >> 10);
+                    s += __shfl_sync(0xffffffffu, tabs[3], lo >> 15);
+                    s += __shfl_sync(0xffffffffu, tabs[4], lo >> 20);
+                    s += __shfl_sync(0xffffffffu, tabs[5], lo >> 25);
+                    s += __shfl_sync(0xffffffffu, tabs[6], (unsigned)(D >> 30));
+                    s += __shfl_sync(0xffffffffu, tabs[7], hi >> 3);
+                    s += __shfl_sync(0xffffffffu, tabs[8], hi >> 8);
+                    s += __shfl_sync(0xffffffffu, tabs[9], hi >> 13);
+                    s += __shfl_sync(0xffffffffu, tabs[10], hi >> 18);
+                    s += __shfl_sync(0xffffffffu, tabs[11], hi >> 23);
+                    s += __shfl_sync(0xffffffffu, tabs[12], hi >> 28);
+                    if (!valid) s = 0x7fffffff;
+                    if (s <= s2) {  // thread-local three smallest, earlier index first on equal scores
+                        if (s < s0) { s2 = s1; i2 = i1; s1 = s0; i1 = i0; s0 = s; i0 = i; }
+                        else if (s < s1) { s2 = s1; i2 = i1; s1 = s; i1 = i; }
+                        else if (s < s2) { s2 = s; i2 = i; }
+                    }
                 }
-                warp_argmin(bs, bi);
-                if (lane == 0) { S.red_s[w][warp] = bs; S.red_i[w][warp] = bi; }
+                int m = s0;
+#pragma unroll
+                for (int x = 16; x; x >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, x));
+                if (lane == 0) S.red32[warp] = m;
+                __syncthreads();  // (B)
+                m = min(min(S.red32[0], S.red32[1]), min(S.red32[2], S.red32[3]));
+                const int lim = m + OSD_WIN;
+                if (s0 <= lim) { const int p = atomicAdd(&S.cand_n[w], 1); if (p < OSD_CAND_CAP) S.cand_i[w][p] = i0; }
+                if (s1 <= lim) { const int p = atomicAdd(&S.cand_n[w], 1); if (p < OSD_CAND_CAP) S.cand_i[w][p] = i1; }
+                if (s2 <= lim) {  // a fourth one may have been dropped by this thread: take the exact path
+                    const int p = atomicAdd(&S.cand_n[w], 1); if (p < OSD_CAND_CAP) S.cand_i[w][p] = i2;
+                    S.cand_ovf[w] = 1;
+                }
+                __syncthreads();  // (C)
+                if (S.cand_ovf[w] || S.cand_n[w] > OSD_CAND_CAP) {
+                    // too many near-ties (e.g. quantised inputs): exact 64-bit sweep through the byte LUTs
+                    build_lut64(S, G, tid);
+                    __syncthreads();
+                    long long bs = 0x7fffffffffffffffll;
+                    int bi = 0x7fffffff;
+                    for (int i = tid; i < a.n_teps; i += OSD_THREADS) {
+                        const long long s = score64<MAXW>(S, G, __ldg(a.teps + i));
+                        if (s < bs) { bs = s; bi = i; }
+                    }
+                    warp_argmin(bs, bi);
+                    if (lane == 0) { S.red_s[w][warp] = bs; S.red_i[w][warp] = bi; }
+                }
             } else {
+                build_lut64(S, G, tid);
+                __syncthreads();
                 // block minima: warp v takes blocks v, v+4, ... of this frame
                 const int64_t fw = f0 + w;
                 for (int blk = warp; blk < a.n_blocks; blk += OSD_FPB) {
@@ -104,17 +183,7 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_kernel(OsdArgs a, const uint6
                     long long bs = 0x7fffffffffffffffll;
                     int bi = 0x7fffffff;
                     for (int i = i0 + lane; i < i1; i += 32) {
-                        const unsigned tw = __ldg(a.teps + i);
-                        unsigned long long D = gd0;
-                        long long s = gbase;
-#pragma unroll
-                        for (int j = 0; j < MAXW; ++j) {
-                            const unsigned t = min((tw >> (8 * j)) & 0xffu, 64u);
-                            D ^= G.prow[t];
-                            s += G.qd[t];
-                        }
-#pragma unroll
-                        for (int b = 0; b < 8; ++b) s += (long long)S.lut[b][(unsigned)(D >> (8 * b)) & 0xffu];
+                        const long long s = score64<MAXW>(S, G, __ldg(a.teps + i));
                         if (s < bs) { bs = s; bi = i; }
                     }
                     warp_argmin(bs, bi);
@@ -129,13 +198,37 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_kernel(OsdArgs a, const uint6
         // ---- outputs (each warp finishes its own frame) ---------------------------------------------------
         if (active) {
             if (!BLOCKS) {
-                long long best_s = S.red_s[warp][0];
-                int best_i = S.red_i[warp][0];
+                long long best_s = 0x7fffffffffffffffll;
+                int best_i = 0x7fffffff;
+                const int nc = S.cand_n[warp];
+                if (S.cand_ovf[warp] || nc > OSD_CAND_CAP) {
+                    best_s = S.red_s[warp][0];
+                    best_i = S.red_i[warp][0];
 #pragma unroll
-                for (int v = 1; v < OSD_FPB; ++v) {
-                    const long long os = S.red_s[warp][v];
-                    const int oi = S.red_i[warp][v];
-                    if (os < best_s || (os == best_s && oi < best_i)) { best_s = os; best_i = oi; }
+                    for (int v = 1; v < OSD_FPB; ++v) {
+                        const long long os = S.red_s[warp][v];
+                        const int oi = S.red_i[warp][v];
+                        if (os < best_s || (os == best_s && oi < best_i)) { best_s = os; best_i = oi; }
+                    }
+                } else if (nc == 1 && !a.best_score_q) {
+                    best_i = S.cand_i[warp][0];  // a single candidate is the exact minimum
+                } else {
+                    // exact scores of the few candidates, warp-cooperative weighted popcount
+                    const long long q_l0 = (long long)F.qlrb[lane], q_l1 = (long long)F.qlrb[lane + 32];
+                    for (int c = 0; c < nc; ++c) {
+                        const int ci = S.cand_i[warp][c];
+                        const unsigned tw = __ldg(a.teps + ci);
+                        unsigned long long D = d0;
+                        long long sm = F.base;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const unsigned t = (tw >> (8 * j)) & 0xffu;
+                            if (t < 64u) { D ^= F.prow[t]; sm += F.qd[t]; }
+                        }
+                        const long long sl = (((D >> lane) & 1ull) ? q_l0 : 0ll) + (((D >> (lane + 32)) & 1ull) ? q_l1 : 0ll);
+                        const long long sc = sm + warp_sum_ll(sl);
+                        if (sc < best_s || (sc == best_s && ci < best_i)) { best_s = sc; best_i = ci; }
+                    }
                 }
                 // re-encode the winner and un-permute
                 unsigned long long D = d0, flip = 0ull;

@@ -18,6 +18,10 @@ struct __align__(16) FrameSm {
     unsigned long long d0;        // order-0 discrepancy on the LRB
     long long base;               // order-0 discrepancy weight on the MRB
     unsigned long long d0m;       // order-0 discrepancy bits on the MRB (0 when both metrics agree)
+    unsigned w32[64];             // floor(q_lrb / 2^30): 32-bit weights of the fast sweep
+    int qd32[66];                 // floor(qd / 2^30), [64] = 0
+    int base32;                   // floor(base / 2^30)
+    int pad32;
     unsigned char pi1[N];         // sorted position -> original index
     unsigned char pos[N];         // permuted position (MRB then LRB) -> sorted position
     unsigned char prow_of[K];     // pivot row of MRB position t
@@ -29,6 +33,10 @@ struct __align__(16) OsdSmem {
     FrameSm fr[OSD_FPB];
     long long red_s[OSD_FPB][OSD_FPB];  // [frame][warp] partial minima
     int red_i[OSD_FPB][OSD_FPB];
+    int red32[OSD_FPB];              // fast sweep: per-warp minima of the 32-bit scores
+    int cand_n[OSD_FPB];             // fast sweep: candidates whose exact score can still be the minimum
+    int cand_ovf[OSD_FPB];
+    int cand_i[OSD_FPB][32];
     int red_stop[OSD_FPB];           // FS: per-warp first stopping TEP index
     long long fs_score[OSD_FPB];     // FS results per frame
     int fs_opt[OSD_FPB], fs_num[OSD_FPB], fs_kind[OSD_FPB];
@@ -300,12 +308,16 @@ __device__ __forceinline__ Prep prepare_frame(const OsdArgs& a, FrameSm& F, cons
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const unsigned d0m = ho[k] ^ hd[k];
-        F.qd[lane + 32 * k] = d0m ? -q[k] : q[k];
+        const long long qdv = d0m ? -q[k] : q[k];
+        F.qd[lane + 32 * k] = qdv;
+        F.qd32[lane + 32 * k] = (int)(qdv >> 30);
         base += d0m ? q[k] : 0ll;
     }
     base = warp_sum_ll(base);
     F.qlrb[lane] = (unsigned long long)q[2];
     F.qlrb[lane + 32] = (unsigned long long)q[3];
+    F.w32[lane] = (unsigned)(q[2] >> 30);
+    F.w32[lane + 32] = (unsigned)(q[3] >> 30);
     F.prow[lane] = myprow[0];
     F.prow[lane + 32] = myprow[1];
     unsigned long long c0 = (ho[0] ? myprow[0] : 0ull) ^ (ho[1] ? myprow[1] : 0ull);
@@ -314,7 +326,7 @@ __device__ __forceinline__ Prep prepare_frame(const OsdArgs& a, FrameSm& F, cons
     ho_mrb = (unsigned long long)__ballot_sync(0xffffffffu, ho[0]) | ((unsigned long long)__ballot_sync(0xffffffffu, ho[1]) << 32);
     const unsigned long long hd_mrb_out = (unsigned long long)__ballot_sync(0xffffffffu, hd[0]) | ((unsigned long long)__ballot_sync(0xffffffffu, hd[1]) << 32);
     d0 = c0 ^ hd_lrb;
-    if (lane == 0) { F.d0 = d0; F.base = base; F.d0m = ho_mrb ^ hd_mrb_out; F.prow[64] = 0ull; F.qd[64] = 0ll; }  // [64]: padded TEP slots (qd aliases cols until here)
+    if (lane == 0) { F.d0 = d0; F.base = base; F.d0m = ho_mrb ^ hd_mrb_out; F.prow[64] = 0ull; F.qd[64] = 0ll; F.qd32[64] = 0; F.base32 = (int)(base >> 30); }  // [64]: padded TEP slots (qd aliases cols until here)
     if (TRUTH && a.truth_bits && a.truth_score_q) {
         long long ts = 0;
 #pragma unroll
