@@ -21,18 +21,26 @@ constexpr int NUM_WS = 4;       // workspace slots (0: device pipeline, 1..3: ho
 // ---- NMS tables (device, built once per handle; reference: the dense H of ms_test.py:126,182) ----
 // Shared-memory layout of one frame in the NMS kernel, in floats:
 //   T[0..127]   per-variable total (sum of incoming cv + w_vc*y), T[128] = +inf (padding edges)
-//   CV[e*64+c]  check->variable message of edge e (0..7) of check c, at float offset NMS_CV_OFF
-//   CV[512] = 0 (padding for variables of low degree), CV[513] = dump slot for padded check edges
+//   CV[e*96 + rot[e] + c]  check->variable message of the edge labelled e (0..7) of check c, at float offset
+//                NMS_CV_OFF.  A lane writes its two checks at consecutive addresses (conflict-free); the labels of
+//                a check's edges and the rotations rot[e] (< 32) are chosen at ldpcb_create so that the variable
+//                side, which gathers its incoming messages in ascending check order, is bank-conflict free too
+//   CV[768] = 0 (padding for variables of low degree), CV[769] = dump slot for padded check edges
 constexpr int NMS_T_FLOATS = 132;
 constexpr int NMS_CV_OFF = NMS_T_FLOATS;
-constexpr int NMS_CV_FLOATS = 516;
-constexpr int NMS_FRAME_FLOATS = NMS_T_FLOATS + NMS_CV_FLOATS;  // 648 floats = 2592 B
+constexpr int NMS_CV_STRIDE = 96;
+constexpr int NMS_CV_ZERO = DC * NMS_CV_STRIDE;      // 768
+constexpr int NMS_CV_DUMP = NMS_CV_ZERO + 1;
+constexpr int NMS_CV_FLOATS = NMS_CV_ZERO + 4;
+constexpr int NMS_FRAME_FLOATS = NMS_T_FLOATS + NMS_CV_FLOATS;  // 904 floats = 3616 B
 
 struct NmsTables {
-    // chk_var[c][e]: variable index of edge e of check c (ascending), 128 = padding
+    // chk_var[c][e]: variable index of the edge labelled e of check c, 128 = padding
     uint8_t chk_var[M][DC];
-    // var_slot[v][d]: CV index (e*64+c) of the d-th incoming edge of variable v, checks ascending
-    // (the summation order of tf.reduce_sum(cv_matrix, 1) restated in oracle/nms_oracle.py); 512 = padding
+    // rot[e]: bank rotation of label e
+    int rot[DC];
+    // var_slot[v][d]: CV index (e*96+rot[e]+c) of the d-th incoming edge of variable v, checks ascending
+    // (the summation order of tf.reduce_sum(cv_matrix, 1) restated in oracle/nms_oracle.py); 768 = padding
     uint16_t var_slot[N][DV];
     // chk_mask[c][w]: bit-packed row c of H (syndrome)
     uint32_t chk_mask[M][4];

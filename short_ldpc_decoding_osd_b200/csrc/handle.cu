@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <limits>
 
@@ -111,37 +112,159 @@ int build_tep_tables(ldpcb_handle* h) {
 }
 
 // ---- code tables ------------------------------------------------------------------------------
+// Choose the edge labels of every check and the per-label bank rotations so that both gathers of the NMS kernel are
+// (nearly) free of shared-memory bank conflicts:
+//   check side    row (q, e): lane l reads T[variable of the edge labelled e of check l + 32q], bank = variable mod 32
+//   variable side row (k, d): lane l reads the d-th incoming message (ascending check order) of variable l + 32k,
+//                 stored at bank (check + rot[label]) mod 32
+// Labels are permuted per "class" = (block row of 16 checks, block column of 16 variables, circulant shift), which
+// keeps the regularity a quasi-cyclic H gives the check side; for an unstructured H every edge is its own class.
+// Simulated annealing on the number of colliding lanes from the natural labelling, deterministic, ~0.2 s, best kept.
+static void optimise_nms_layout(const uint8_t* Hm, int label_of[M][N], int rot[DC]) {
+    std::vector<std::vector<int>> chk(M), var(N);
+    for (int c = 0; c < M; ++c)
+        for (int v = 0; v < N; ++v)
+            if (Hm[c * N + v]) { chk[c].push_back(v); var[v].push_back(c); }
+    // classes per block row
+    struct Cls { int C, s; std::vector<std::pair<int, int>> edges; };
+    std::vector<std::vector<Cls>> cls(M / 16);
+    bool structured = true;
+    for (int R = 0; R < M / 16; ++R) {
+        for (int c = 16 * R; c < 16 * R + 16; ++c)
+            for (int v : chk[c]) {
+                const int C = v / 16, sft = ((v % 16) - (c % 16) + 16) % 16;
+                Cls* f = nullptr;
+                for (auto& x : cls[R]) if (x.C == C && x.s == sft) f = &x;
+                if (!f) { cls[R].push_back({C, sft, {}}); f = &cls[R].back(); }
+                f->edges.push_back({c, v});
+            }
+        if ((int)cls[R].size() > DC) structured = false;
+        for (auto& x : cls[R]) if (x.edges.size() != 16) structured = false;
+    }
+    // natural labelling
+    for (int c = 0; c < M; ++c)
+        for (size_t e = 0; e < chk[c].size(); ++e) label_of[c][chk[c][e]] = (int)e;
+    for (int e = 0; e < DC; ++e) rot[e] = 0;
+    if (structured) {  // start from one label per class (ascending block column, shift)
+        for (int R = 0; R < M / 16; ++R) {
+            std::sort(cls[R].begin(), cls[R].end(), [](const Cls& a, const Cls& b) { return a.C != b.C ? a.C < b.C : a.s < b.s; });
+            for (size_t i = 0; i < cls[R].size(); ++i)
+                for (auto& e : cls[R][i].edges) label_of[e.first][e.second] = (int)i;
+        }
+    }
+    auto cost = [&]() {
+        int tot = 0;
+        for (int k = 0; k < 4; ++k)
+            for (int d = 0; d < DV; ++d) {
+                int cnt[32] = {0};
+                for (int l = 0; l < 32; ++l) {
+                    const int v = l + 32 * k;
+                    if (d < (int)var[v].size()) { const int c = var[v][d]; ++cnt[(c + rot[label_of[c][v]]) & 31]; }
+                }
+                for (int b = 0; b < 32; ++b) tot += cnt[b] > 1 ? cnt[b] - 1 : 0;
+            }
+        for (int q = 0; q < 2; ++q) {
+            int cnt[DC][32];
+            memset(cnt, 0, sizeof cnt);
+            for (int l = 0; l < 32; ++l) {
+                const int c = l + 32 * q;
+                for (int v : chk[c]) ++cnt[label_of[c][v]][v & 31];
+            }
+            for (int e = 0; e < DC; ++e)
+                for (int b = 0; b < 32; ++b) tot += cnt[e][b] > 1 ? cnt[e][b] - 1 : 0;
+        }
+        return tot;
+    };
+    uint64_t rng = 0x9E3779B97F4A7C15ull;
+    auto next = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
+    auto unif = [&]() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); };
+    int cur = cost(), best = cur, best_rot[DC];
+    static thread_local int best_label[M][N];
+    memcpy(best_label, label_of, sizeof best_label);
+    memcpy(best_rot, rot, sizeof best_rot);
+    double T = 2.0;
+    for (int it = 0; it < 60000 && best > 0; ++it) {
+        T = std::max(0.05, T * 0.9999);
+        if (it % 15000 == 14999) {  // restart from the best so far with a warm temperature
+            memcpy(label_of, best_label, sizeof best_label);
+            memcpy(rot, best_rot, sizeof best_rot);
+            cur = best;
+            T = 1.0;
+        }
+        if (next() % 5 < 2) {
+            const int e = (int)(next() % DC), old = rot[e];
+            rot[e] = (int)(next() % 32);
+            const int nw = cost();
+            if (nw <= cur || unif() < exp((cur - nw) / T)) cur = nw; else rot[e] = old;
+        } else if (structured) {
+            const int R = (int)(next() % (M / 16));
+            const int a = (int)(next() % cls[R].size()), b = (int)(next() % cls[R].size());
+            if (a == b) continue;
+            const int la = label_of[cls[R][a].edges[0].first][cls[R][a].edges[0].second];
+            const int lb = label_of[cls[R][b].edges[0].first][cls[R][b].edges[0].second];
+            auto apply = [&](int x, int y) {
+                for (auto& e : cls[R][a].edges) label_of[e.first][e.second] = x;
+                for (auto& e : cls[R][b].edges) label_of[e.first][e.second] = y;
+            };
+            apply(lb, la);
+            const int nw = cost();
+            if (nw <= cur || unif() < exp((cur - nw) / T)) cur = nw; else apply(la, lb);
+        } else {
+            const int c = (int)(next() % M), d = (int)chk[c].size();
+            const int v1 = chk[c][next() % d], v2 = chk[c][next() % d];
+            if (v1 == v2) continue;
+            std::swap(label_of[c][v1], label_of[c][v2]);
+            const int nw = cost();
+            if (nw <= cur || unif() < exp((cur - nw) / T)) cur = nw; else std::swap(label_of[c][v1], label_of[c][v2]);
+        }
+        if (cur < best) {
+            best = cur;
+            memcpy(best_label, label_of, sizeof best_label);
+            memcpy(best_rot, rot, sizeof best_rot);
+        }
+    }
+    memcpy(label_of, best_label, sizeof best_label);
+    memcpy(rot, best_rot, sizeof best_rot);
+}
+
 static int build_code_tables(ldpcb_handle* h) {
     NmsTables& t = h->nms_host;
     memset(&t, 0, sizeof t);
-    int pos_in_check[M][N];
+    static thread_local int label_of[M][N];
     for (int c = 0; c < M; ++c) {
         int e = 0;
         for (int v = 0; v < N; ++v) {
-            pos_in_check[c][v] = -1;
             if (h->H[c * N + v]) {
                 if (e >= DC) return set_error(h, LDPCB_ERR_SHAPE, "check %d has degree > %d", c, DC);
-                t.chk_var[c][e] = (uint8_t)v;
-                pos_in_check[c][v] = e;
                 t.chk_mask[c][v >> 5] |= 1u << (v & 31);
                 ++e;
             }
         }
         if (e < 2) return set_error(h, LDPCB_ERR_SHAPE, "check %d has degree < 2", c);
-        for (; e < DC; ++e) t.chk_var[c][e] = 128;
+    }
+    for (int v = 0; v < N; ++v) {
+        int d = 0;
+        for (int c = 0; c < M; ++c) d += h->H[c * N + v];
+        if (d > DV) return set_error(h, LDPCB_ERR_SHAPE, "variable %d has degree > %d", v, DV);
+    }
+    optimise_nms_layout(h->H, label_of, t.rot);
+    for (int c = 0; c < M; ++c) {
+        for (int e = 0; e < DC; ++e) t.chk_var[c][e] = 128;
+        for (int v = 0; v < N; ++v)
+            if (h->H[c * N + v]) t.chk_var[c][label_of[c][v]] = (uint8_t)v;
     }
     t.max_var_deg_lo = t.max_var_deg_hi = 0;
     for (int v = 0; v < N; ++v) {
         int d = 0;
         for (int c = 0; c < M; ++c) {
             if (h->H[c * N + v]) {
-                if (d >= DV) return set_error(h, LDPCB_ERR_SHAPE, "variable %d has degree > %d", v, DV);
-                t.var_slot[v][d++] = (uint16_t)(pos_in_check[c][v] * M + c);
+                const int e = label_of[c][v];
+                t.var_slot[v][d++] = (uint16_t)(e * NMS_CV_STRIDE + t.rot[e] + c);
             }
         }
         int& mx = (v < 64) ? t.max_var_deg_lo : t.max_var_deg_hi;
         mx = std::max(mx, d);
-        for (; d < DV; ++d) t.var_slot[v][d] = 512;
+        for (; d < DV; ++d) t.var_slot[v][d] = NMS_CV_ZERO;
     }
     // G columns, and H.G^T = 0, rank(G) = K
     for (int j = 0; j < N; ++j) {

@@ -27,9 +27,9 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
     return r;
 }
 
-// REG8: every check has degree 8 (CCSDS): edge e of check c is stored at CV[e*64+c], no padding slots needed
+// REG8: every check has degree 8 (CCSDS): the edge labelled e of check c is stored at CV[e*96+rot[e]+c], no padding slots
 template <int DVA, int DVB, bool REG8, bool TRAJ, bool EARLY>
-__global__ void __launch_bounds__(NMS_THREADS) nms_kernel(NmsArgs a, const NmsTables* __restrict__ tab) {
+__global__ void __launch_bounds__(NMS_THREADS, 3) nms_kernel(NmsArgs a, const NmsTables* __restrict__ tab) {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(NmsArgs a, const NmsTa
         for (int e = 0; e < DC; ++e) {
             const int v = tab->chk_var[c][e];
             tv[q][e] = v;
-            if (!REG8) cs[q][e] = (v < N) ? (e * M + c) : 513;
+            if (!REG8) cs[q][e] = (v < N) ? (e * NMS_CV_STRIDE + tab->rot[e] + c) : NMS_CV_DUMP;
         }
     }
     int vs[4][DVA > DVB ? DVA : DVB];
@@ -64,10 +64,13 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(NmsArgs a, const NmsTa
             for (int w = 0; w < 4; ++w) mk[q][w] = tab->chk_mask[lane + 32 * q][w];
     }
 
+    int rot[DC];  // uniform: bank rotation of each edge label
+#pragma unroll
+    for (int e = 0; e < DC; ++e) rot[e] = tab->rot[e];
     if (lane == 0) {
         T[128] = __int_as_float(0x7f800000);  // +inf feeds padded check edges
-        CV[512] = 0.0f;                       // padded variable edges add zero
-        CV[513] = 0.0f;
+        CV[NMS_CV_ZERO] = 0.0f;               // padded variable edges add zero
+        CV[NMS_CV_DUMP] = 0.0f;
     }
     const bool same_w = (a.w_vc == a.w_marg);
     const int64_t gw = (int64_t)blockIdx.x * NMS_WARPS + warp;
@@ -137,12 +140,17 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(NmsArgs a, const NmsTa
                 for (int e = 1; e < DC; ++e) sx ^= __float_as_uint(x[e]);
                 sx &= 0x80000000u;
                 const unsigned u1 = __float_as_uint(a1) ^ sx, u2 = __float_as_uint(a2) ^ sx;
+                const unsigned du = u1 - u2;
 #pragma unroll
                 for (int e = 0; e < DC; ++e) {
-                    const unsigned u = (ax[e] > m1) ? u1 : u2;  // strict '>' (ms_test.py:206)
+                    // select u1 where |x| > m1 (strict, ms_test.py:206) else u2, with the compare and the blend on the
+                    // FMA pipe (the ALU pipe is the busy one): m1 - |x| is negative exactly when |x| > m1
+                    const unsigned gt = __float_as_uint(__fsub_rn(m1, ax[e])) >> 31;
+                    unsigned u;
+                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(u) : "r"(gt), "r"(du), "r"(u2));
                     const float o = __uint_as_float(u ^ (__float_as_uint(x[e]) & 0x80000000u));
                     cvo[q][e] = o;
-                    CV[REG8 ? (e * M + lane + 32 * q) : cs[q][e]] = o;
+                    CV[REG8 ? (e * NMS_CV_STRIDE + rot[e] + lane + 32 * q) : cs[q][e]] = o;
                 }
             }
             __syncwarp();
