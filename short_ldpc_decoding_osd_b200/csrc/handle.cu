@@ -104,8 +104,11 @@ int build_tep_tables(ldpcb_handle* h) {
             if (kind == LDPCB_TEP_CONV) build_conv(order, t.host); else build_fs(order, t.host);
             t.n = (int)t.host.size();
             t.maxw = order < 1 ? 1 : order;
-            LDPCB_CUDA(h, cudaMalloc(&t.dev, sizeof(uint32_t) * t.n));
-            LDPCB_CUDA(h, cudaMemcpy(t.dev, t.host.data(), sizeof(uint32_t) * t.n, cudaMemcpyHostToDevice));
+            // the device copy is padded with 128 "no position" words: the sweep loads whole 128-TEP tiles unconditionally
+            std::vector<uint32_t> padded(t.host);
+            padded.resize(t.n + 128, 0xFFFFFFFFu);
+            LDPCB_CUDA(h, cudaMalloc(&t.dev, sizeof(uint32_t) * padded.size()));
+            LDPCB_CUDA(h, cudaMemcpy(t.dev, padded.data(), sizeof(uint32_t) * padded.size(), cudaMemcpyHostToDevice));
         }
     }
     return LDPCB_OK;

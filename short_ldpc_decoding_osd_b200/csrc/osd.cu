@@ -90,7 +90,19 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_kernel(OsdArgs a, const uint6
         const unsigned long long hd_lrb = P.hd_lrb, ho_mrb = P.ho_mrb, d0 = P.d0;
         const int E = P.E;
         // ---- 5./6. sweep: the four warps take the prepared frames in turn -------------------------------------
-        if (!BLOCKS && active && lane == 0) { S.cand_n[warp] = 0; S.cand_ovf[warp] = 0; }
+        if (!BLOCKS && active) {
+            if (lane == 0) { S.cand_n[warp] = 0; S.cand_ovf[warp] = 0; }
+            __syncwarp();
+            // 5-bit chunk tables of the 32-bit LRB weights: tabs[j][e] = sum of w32[5j+i] over the set bits i of e
+#pragma unroll
+            for (int j = 0; j < 13; ++j) {
+                int v = 0;
+#pragma unroll
+                for (int i = 0; i < 5; ++i)
+                    if (5 * j + i < 64) v += ((lane >> i) & 1) ? (int)F.w32[5 * j + i] : 0;
+                S.tabs[warp][j][lane] = v;
+            }
+        }
         const int nfr = (int)((nframes - f0) < OSD_FPB ? (nframes - f0) : OSD_FPB);
         for (int w = 0; w < nfr; ++w) {
             const FrameSm& G = S.fr[w];
@@ -103,20 +115,15 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_kernel(OsdArgs a, const uint6
                 // S32 <= min S32 + OSD_WIN; those few are re-scored exactly at output.
                 int tabs[13];
 #pragma unroll
-                for (int j = 0; j < 13; ++j) {
-                    int v = 0;
-#pragma unroll
-                    for (int i = 0; i < 5; ++i)
-                        if (5 * j + i < 64) v += ((lane >> i) & 1) ? (int)G.w32[5 * j + i] : 0;
-                    tabs[j] = v;
-                }
+                for (int j = 0; j < 13; ++j) tabs[j] = S.tabs[w][j][lane];  // built by the frame's owner warp
                 const unsigned long long gd0 = G.d0;
                 const int gb32 = G.base32;
                 int s0 = 0x7fffffff, s1 = 0x7fffffff, s2 = 0x7fffffff, i0 = 0x7fffffff, i1 = 0x7fffffff, i2 = 0x7fffffff;
-                for (int ib = warp * 32; ib < a.n_teps; ib += OSD_THREADS) {
+                int wm = 0x7fffffff - OSD_WIN;  // warp-wide running minimum: only TEPs within the window of it can matter
+                const uint32_t* tp = a.teps + warp * 32 + lane;  // the table is padded to whole 128-TEP tiles
+                for (int ib = warp * 32; ib < a.n_teps; ib += OSD_THREADS, tp += OSD_THREADS) {
                     const int i = ib + lane;
-                    const bool valid = i < a.n_teps;
-                    const unsigned tw = valid ? __ldg(a.teps + i) : 0xffffffffu;
+                    const unsigned tw = __ldg(tp);
                     unsigned long long D = gd0;
                     int s = gb32;
 #pragma unroll
@@ -139,8 +146,9 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_kernel(OsdArgs a, const uint6
                     s += __shfl_sync(0xffffffffu, tabs[10], hi >> 18);
                     s += __shfl_sync(0xffffffffu, tabs[11], hi >> 23);
                     s += __shfl_sync(0xffffffffu, tabs[12], hi >> 28);
-                    if (!valid) s = 0x7fffffff;
-                    if (s <= s2) {  // thread-local three smallest, earlier index first on equal scores
+                    if (i >= a.n_teps) s = 0x7fffffff;
+                    wm = min(wm, __reduce_min_sync(0xffffffffu, s));
+                    if (s <= wm + OSD_WIN && s <= s2) {  // thread-local three smallest, earlier index first on equal scores
                         if (s < s0) { s2 = s1; i2 = i1; s1 = s0; i1 = i0; s0 = s; i0 = i; }
                         else if (s < s1) { s2 = s1; i2 = i1; s1 = s; i1 = i; }
                         else if (s < s2) { s2 = s; i2 = i; }

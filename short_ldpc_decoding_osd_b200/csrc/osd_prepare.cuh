@@ -37,6 +37,7 @@ struct __align__(16) OsdSmem {
     int cand_n[OSD_FPB];             // fast sweep: candidates whose exact score can still be the minimum
     int cand_ovf[OSD_FPB];
     int cand_i[OSD_FPB][32];
+    int tabs[OSD_FPB][13][32];       // fast sweep: 5-bit chunk tables of each frame (entry = lane)
     int red_stop[OSD_FPB];           // FS: per-warp first stopping TEP index
     long long fs_score[OSD_FPB];     // FS results per frame
     int fs_opt[OSD_FPB], fs_num[OSD_FPB], fs_kind[OSD_FPB];

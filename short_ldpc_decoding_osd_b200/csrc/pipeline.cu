@@ -269,14 +269,14 @@ extern "C" int ldpcb_osd_sweep_host(ldpcb_t* h, const float* upd_order_llr_host,
     }
     cudaStream_t st = h->streams[0];
     Carver probe(nullptr);
-    probe.take<uint32_t>((size_t)n_teps);
+    probe.take<uint32_t>((size_t)n_teps + 128);
     const int64_t chunk = std::min<int64_t>(B, HOST_CHUNK);
     probe.take<float>((size_t)chunk * N); probe.take<float>((size_t)chunk * N); probe.take<uint64_t>((size_t)chunk * K);
     probe.take<uint32_t>((size_t)chunk * 4); probe.take<int32_t>((size_t)chunk); probe.take<int64_t>((size_t)chunk); probe.take<int32_t>((size_t)chunk);
     int s = ensure_ws(h, 1, probe.off + 256);
     if (s != LDPCB_OK) return s;
     Carver c(h->ws[1].buf);
-    uint32_t* teps = c.take<uint32_t>((size_t)n_teps);
+    uint32_t* teps = c.take<uint32_t>((size_t)n_teps + 128);  // padded like the built-in tables
     float* ol = c.take<float>((size_t)chunk * N);
     float* sl = c.take<float>((size_t)chunk * N);
     uint64_t* rg = c.take<uint64_t>((size_t)chunk * K);
@@ -284,6 +284,7 @@ extern "C" int ldpcb_osd_sweep_host(ldpcb_t* h, const float* upd_order_llr_host,
     int32_t* bt = c.take<int32_t>((size_t)chunk);
     int64_t* bq = c.take<int64_t>((size_t)chunk);
     int32_t* ex = c.take<int32_t>((size_t)chunk);
+    LDPCB_CUDA(h, cudaMemsetAsync(teps + n_teps, 0xFF, sizeof(uint32_t) * 128, st));
     LDPCB_CUDA(h, cudaMemcpyAsync(teps, teps_host, sizeof(uint32_t) * n_teps, cudaMemcpyHostToDevice, st));
     for (int64_t b0 = 0; b0 < B; b0 += chunk) {
         const int64_t nb = std::min(chunk, B - b0);
