@@ -174,6 +174,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     devs = f"cuda:{local_rank}"
     if world > 1:
+        # keep stdout to the one JSON line: NCCL's version banner and debug output go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(devs))
     code = Code()
     h = _lib.Handle(code.H, code.G, device=local_rank)
