@@ -279,6 +279,24 @@ int ldpcb_dia_fir(ldpcb_t* h, const float* traj_dev, int64_t B, int n_rows, cons
                   float bias, float* out_dev, void* stream);
 
 /*
+ * DL sliding-window early termination over the block minima of ldpcb_osd_block_minima.  Replaces the window
+ * bookkeeping of osd.sliding_osd (DL_OSD_Testing_serial/ordered_statistics_decoding.py:186-219) with
+ * sliding_window_ops (:141-151) and the classifier Predict_outlier_light (nn_net.py:136-149: Dense(w+1, no
+ * bias, linear) -> Dense(2, no bias, softmax), stop when p[1] > soft_margin).
+ *   block_min_q_dev [B,n_blocks], score_exp_dev [B], truth_score_q_dev [B] (may be NULL => success = 0)
+ *   win_width <= 8 (reference: 5), n_blocks <= 128 (reference: decoding_length 30)
+ *   W1_host [(w+1)*(w+1)] and W2_host [(w+1)*2] row-major Keras kernels (input index first)
+ *   acc_block_size_host [n_blocks+1] cumulative TEP counts (nn_testing.py:156)
+ *   success_dev [B] uint8, windows_dev [B], complexity_dev [B] out (each may be NULL);
+ *   counters_dev [4] uint64 accumulated (may be NULL): successes, failures, windows_sum, complexity_sum
+ */
+int ldpcb_dl_window_policy(ldpcb_t* h, const int64_t* block_min_q_dev, const int32_t* score_exp_dev,
+                           const int64_t* truth_score_q_dev, int64_t B, int n_blocks, int win_width,
+                           const float* W1_host, const float* W2_host, float soft_margin,
+                           const int32_t* acc_block_size_host, uint8_t* success_dev, int32_t* windows_dev,
+                           int32_t* complexity_dev, uint64_t* counters_dev, void* stream);
+
+/*
  * FER/BER tallies (get_eval, ms_test.py:36-54; convention_osd.py:67-75).  Adds to counters_dev.
  *   nms_bits_dev [B,4], syndrome_nz_dev [B], iters_used_dev [B] (may be NULL): NMS results
  *   final_bits_dev [B,4] (may be NULL): decisions after OSD (equal to nms_bits for frames not sent)

@@ -1,5 +1,7 @@
 // Small data-parallel kernels around the two decoders: FER/BER tallies, stable compaction of the
 // detected failures, row gather, DIA FIR.
+#include <cstring>
+
 #include "common.cuh"
 #include "internal.cuh"
 
@@ -245,6 +247,85 @@ __global__ void __launch_bounds__(256) dia_fir_kernel(const float4* __restrict__
     }
 }
 
+
+// ---- DL sliding-window early termination -----------------------------------------------------------------
+// osd.sliding_osd's window bookkeeping (DL_OSD_Testing_serial/ordered_statistics_decoding.py:186-219) with
+// sliding_window_ops (:141-151) and the 6 -> 6 -> 2 classifier Predict_outlier_light (nn_net.py:136-149), one
+// thread per frame over the <= 128 block minima the sweep kernel produced.  Minima are compared as exact integers;
+// the classifier sees them as fp32 (q * 2^(E-54)).
+constexpr int DLW_MAX_WIDTH = 8;
+constexpr int DLW_MAX_BLOCKS = 128;
+struct DlwParams {
+    float W1[(DLW_MAX_WIDTH + 1) * (DLW_MAX_WIDTH + 1)];
+    float W2[(DLW_MAX_WIDTH + 1) * 2];
+    int acc[DLW_MAX_BLOCKS + 1];
+    float soft_margin;
+    int width, n_blocks;
+};
+
+__global__ void __launch_bounds__(256) dl_window_kernel(const long long* __restrict__ bm, const int* __restrict__ ex,
+                                                        const long long* __restrict__ truth, int64_t B, DlwParams p,
+                                                        uint8_t* success, int* windows, int* complexity,
+                                                        unsigned long long* counters) {
+    __shared__ unsigned long long sh[4];
+    if (threadIdx.x < 4) sh[threadIdx.x] = 0ull;
+    __syncthreads();
+    unsigned long long c_s = 0, c_f = 0, c_w = 0, c_c = 0;
+    const int W = p.width, nb = p.n_blocks, in_w = W + 1;
+    for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < B; f += (int64_t)gridDim.x * blockDim.x) {
+        const long long* m = bm + f * nb;
+        const double scale = __hiloint2double((1023 + ex[f] - 54) << 20, 0);
+        long long win[DLW_MAX_WIDTH];
+        long long gmin = 0x7fffffffffffffffll;
+        for (int j = 0; j < W; ++j) { win[j] = m[j]; gmin = win[j] < gmin ? win[j] : gmin; }
+        int deep = W;
+        for (int k = 0; k < nb - W + 1; ++k) {
+            deep = k + W;
+            if (k != 0) {
+                const long long ms = m[W + k - 1];
+                for (int j = 0; j + 1 < W; ++j) win[j] = win[j + 1];
+                win[W - 1] = ms;
+                if (ms > gmin) continue;
+            }
+            // sorted window (ascending) + position k -> classifier
+            float x[DLW_MAX_WIDTH + 1];
+            long long srt[DLW_MAX_WIDTH];
+            for (int j = 0; j < W; ++j) {
+                long long v = win[j];
+                int q = j;
+                while (q > 0 && srt[q - 1] > v) { srt[q] = srt[q - 1]; --q; }
+                srt[q] = v;
+            }
+            for (int j = 0; j < W; ++j) x[j] = (float)((double)srt[j] * scale);
+            x[W] = (float)k;
+            float o0 = 0.0f, o1 = 0.0f;
+            for (int u = 0; u < in_w; ++u) {
+                float hsum = 0.0f;
+                for (int j = 0; j < in_w; ++j) hsum = __fmaf_rn(x[j], p.W1[j * in_w + u], hsum);
+                o0 = __fmaf_rn(hsum, p.W2[u * 2 + 0], o0);
+                o1 = __fmaf_rn(hsum, p.W2[u * 2 + 1], o1);
+            }
+            const float mx = fmaxf(o0, o1);
+            const float e0 = expf(o0 - mx), e1 = expf(o1 - mx);
+            const float p1 = e1 / (e0 + e1);
+            if (srt[0] < gmin) gmin = srt[0];
+            if (p1 > p.soft_margin) break;
+        }
+        const int nwin = deep - W + 1;
+        const int cx = p.acc[deep];
+        const bool ok = truth ? (gmin == truth[f]) : false;
+        if (success) success[f] = ok ? 1 : 0;
+        if (windows) windows[f] = nwin;
+        if (complexity) complexity[f] = cx;
+        c_s += ok; c_f += !ok; c_w += nwin; c_c += cx;
+    }
+    if (counters) {
+        block_add(sh, 0, c_s); block_add(sh, 1, c_f); block_add(sh, 2, c_w); block_add(sh, 3, c_c);
+        __syncthreads();
+        if (threadIdx.x < 4 && sh[threadIdx.x]) atomicAdd(&counters[threadIdx.x], sh[threadIdx.x]);
+    }
+}
+
 }  // namespace ldpcb
 
 using namespace ldpcb;
@@ -303,5 +384,32 @@ extern "C" int ldpcb_dia_fir(ldpcb_t* h, const float* traj_dev, int64_t B, int n
     int64_t cap = (int64_t)h->sm_count * 8;
     dia_fir_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>((const float4*)traj_dev, B, n_rows, taps, bias, (float4*)out_dev);
     LDPCB_LAUNCH_CHECK(h, "dia_fir_kernel");
+    return LDPCB_OK;
+}
+
+extern "C" int ldpcb_dl_window_policy(ldpcb_t* h, const int64_t* block_min_q_dev, const int32_t* score_exp_dev,
+                                      const int64_t* truth_score_q_dev, int64_t B, int n_blocks, int win_width,
+                                      const float* W1_host, const float* W2_host, float soft_margin,
+                                      const int32_t* acc_block_size_host, uint8_t* success_dev, int32_t* windows_dev,
+                                      int32_t* complexity_dev, uint64_t* counters_dev, void* stream) {
+    if (!h) return LDPCB_ERR_ARG;
+    if (B < 0 || win_width < 1 || win_width > DLW_MAX_WIDTH || n_blocks < win_width || n_blocks > DLW_MAX_BLOCKS)
+        return set_error(h, LDPCB_ERR_ARG, "ldpcb_dl_window_policy: B=%lld n_blocks=%d win_width=%d out of range", (long long)B, n_blocks, win_width);
+    if (!block_min_q_dev || !score_exp_dev || !W1_host || !W2_host || !acc_block_size_host)
+        return set_error(h, LDPCB_ERR_ARG, "ldpcb_dl_window_policy: NULL argument");
+    if (B == 0) return LDPCB_OK;
+    DlwParams p;
+    memset(&p, 0, sizeof p);
+    const int in_w = win_width + 1;
+    for (int i = 0; i < in_w * in_w; ++i) p.W1[i] = W1_host[i];
+    for (int i = 0; i < in_w * 2; ++i) p.W2[i] = W2_host[i];
+    for (int i = 0; i <= n_blocks; ++i) p.acc[i] = acc_block_size_host[i];
+    p.soft_margin = soft_margin; p.width = win_width; p.n_blocks = n_blocks;
+    int64_t want = (B + 255) / 256;
+    int64_t cap = (int64_t)h->sm_count * 8;
+    dl_window_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+        (const long long*)block_min_q_dev, score_exp_dev, (const long long*)truth_score_q_dev, B, p, success_dev, windows_dev,
+        complexity_dev, (unsigned long long*)counters_dev);
+    LDPCB_LAUNCH_CHECK(h, "dl_window_kernel");
     return LDPCB_OK;
 }

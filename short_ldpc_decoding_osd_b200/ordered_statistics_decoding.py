@@ -12,9 +12,9 @@ What runs where:
   both give the same MRB set, and the DL outputs (success, windows, complexity) do not depend on the order of
   the LRB, which is the only thing that differs (tests/test_oracle_golden.py checks it against the
   reference's own H-based code).
-* Host (this module): the window bookkeeping of ``sliding_osd`` (``:164-220``) over the <= 30 block minima of a
-  frame and the 6 -> 6 -> 2 window classifier ``fcn`` (any callable; ``nn_net.Predict_outlier_light`` mirrors
-  the reference's).  Success is ``global_min == discrepancy_sum_truth`` evaluated on exact integers; the
+* The window bookkeeping of ``sliding_osd`` (``:164-220``) over the <= 30 block minima of a frame and the
+  6 -> 6 -> 2 window classifier: on the GPU (ldpcb_dl_window_policy, one thread per frame) when ``fcn`` is a
+  ``nn_net.Predict_outlier_light`` (it exposes its two kernels), on the host for an arbitrary callable.  Success is ``global_min == discrepancy_sum_truth`` evaluated on exact integers; the
   reference's fp32 equality can report false failures (see the golden test).
 """
 from __future__ import annotations
@@ -126,8 +126,30 @@ class osd:
         torch.cuda.synchronize()
         return bm.cpu().numpy(), ts.cpu().numpy(), ex.cpu().numpy(), pm.cpu().numpy()
 
+    def sliding_osd_gpu(self, fcn, input_list, inputs, labels, tep_info):
+        """sliding_osd with the window policy on the GPU too (ldpcb_dl_window_policy); `fcn` must expose the two
+        Keras kernels as W1 [(w+1),(w+1)] and W2 [(w+1),2] (nn_net.Predict_outlier_light)."""
+        import torch  # device memory carrier only
+
+        teps_list, acc_block_size = tep_info
+        width = GL.get_map("sliding_win_width")
+        bm, truth_q, ex, _ = self.block_minima(input_list, inputs, labels, tep_info)
+        h = get_handle()
+        dev = f"cuda:{h.device}"
+        B, nb = bm.shape
+        cnt = torch.zeros(4, dtype=torch.int64, device=dev)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+        h.call("ldpcb_dl_window_policy", t(bm), t(ex), t(truth_q), B, nb, int(width),
+               np.ascontiguousarray(fcn.W1, dtype=np.float32), np.ascontiguousarray(fcn.W2, dtype=np.float32),
+               float(GL.get_map("soft_margin")), np.ascontiguousarray(acc_block_size, dtype=np.int32), None, None, None, cnt, None)
+        torch.cuda.synchronize()
+        c = cnt.cpu().numpy()
+        return int(c[0]), int(c[1]), int(c[2]), int(c[3])
+
     # ordered_statistics_decoding.py:164-220
     def sliding_osd(self, fcn, input_list, inputs, labels, tep_info):
+        if hasattr(fcn, "W1") and hasattr(fcn, "W2"):
+            return self.sliding_osd_gpu(fcn, input_list, inputs, labels, tep_info)
         teps_list, acc_block_size = tep_info
         width = GL.get_map("sliding_win_width")
         bm, truth_q, ex, _ = self.block_minima(input_list, inputs, labels, tep_info)

@@ -165,6 +165,15 @@ def test_dl_sliding_osd_matches_reference(handle, code, golden_dir):
         assert (w, c) == (rw, rc)            # windows visited and TEP complexity: identical policy trace
         if rs:                                # fp32 equality may report a false failure (frame 7, see the oracle test)
             assert s == 1
+    # the same policy on the GPU: the fixture's classifier as Predict_outlier_light kernels (bias folded into W2 via k? no:
+    # the fixture adds a constant to logit 0; a constant column cannot be expressed, so compare GPU vs host on a pure-kernel net)
+    from short_ldpc_decoding_osd_b200 import nn_net as NN
+
+    net = NN.Predict_outlier_light(5, W1=np.eye(6, dtype=np.float32), W2=np.array([[0, -0.5], [0, 0.5], [0, 0], [0, 0], [0, 0], [0, 0.15]], np.float32))
+    host = [osd.__class__.sliding_osd(osd, (lambda x: net(x)), input_list[13 * i:13 * i + 13], g["new_inputs"][i:i + 1], g["labels"][i:i + 1], tep_info) for i in range(B)]
+    gpu = osd.sliding_osd(net, input_list, g["new_inputs"], g["labels"], tep_info)
+    assert gpu == tuple(int(sum(x[j] for x in host)) for j in range(4))
+    assert len({x[2] for x in host}) > 1  # the policy actually stops at different depths
     # DIA FIR drop-in reproduces the fixture's ordering metric
     from short_ldpc_decoding_osd_b200 import nn_net
 
