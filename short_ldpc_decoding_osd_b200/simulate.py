@@ -136,6 +136,77 @@ def run_point(handle, ebn0_db: float, total_frames: int, seed: int = 0, osd_orde
     return Tallies(total)
 
 
+def run_point_dl(handle, ebn0_db: float, total_frames: int, tep_info, taps, bias: float, W1, W2, soft_margin: float = 0.9,
+                 win_width: int = 5, seed: int = 0, iters: int = 12, alpha: float = 0.66943514, chunk: int = 1 << 20,
+                 rank: int = 0, world: int = 1):
+    """One Eb/N0 point of the DL scheme (BASELINE config 4), everything on the device: generate -> NMS -> detected
+    failures re-decoded with their 13-row trajectories -> DIA FIR (ordering metric) -> block minima along the
+    decoding path, scored against the channel LLR -> sliding-window policy.  Mirrors Ldpc_128_testing followed by
+    DL_OSD_Testing_serial/nn_testing.Testing_OSD (:159-256).  tep_info = (list of int[T_b,64] blocks over DL MRB
+    indices, cumulative sizes) as nn_testing.generate_teps returns.  -> (Tallies of the NMS stage, dict of DL sums)."""
+    import torch
+
+    from .ordered_statistics_decoding import FLAGS_DL, pack_dl_teps
+
+    dev = f"cuda:{handle.device}"
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    teps_list, acc = tep_info
+    packed = torch.from_numpy(np.concatenate([pack_dl_teps(b) for b in teps_list]).view(np.int32)).to(dev)
+    starts = torch.from_numpy(np.asarray(acc, dtype=np.int32)).to(dev)
+    nb = len(teps_list)
+    taps = np.ascontiguousarray(taps, dtype=np.float32)
+    rows = iters + 1
+    W1 = np.ascontiguousarray(W1, dtype=np.float32)
+    W2 = np.ascontiguousarray(W2, dtype=np.float32)
+    acc_np = np.ascontiguousarray(acc, dtype=np.int32)
+    counters = torch.zeros(_lib.NUM_COUNTERS, dtype=torch.int64, device=dev)
+    dl = torch.zeros(4, dtype=torch.int64, device=dev)
+    tot = np.zeros(_lib.NUM_COUNTERS, dtype=np.uint64)
+    tot_dl = np.zeros(4, dtype=np.uint64)
+    done = 0
+    e = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)  # noqa: E731
+    while done < total_frames:
+        n = min(chunk, total_frames - done)
+        a, b = shard_range(n, rank, world)
+        m = b - a
+        counters.zero_()
+        dl.zero_()
+        if m > 0:
+            llr, truth, bits = e((m, 128), torch.float32), e((m, 4), torch.int32), e((m, 4), torch.int32)
+            its, syn = e((m,), torch.uint8), e((m,), torch.uint8)
+            idx, cnt = e((m,), torch.int32), e((1,), torch.int32)
+            handle.call("ldpcb_gen_frames", int(seed), int(done + a), m, float(ebn0_db), llr, truth, stream)
+            handle.call("ldpcb_nms_decode", llr, m, iters, float(alpha), 1.0, 1.0, 0, bits, its, syn, None, stream)
+            handle.call("ldpcb_tally", bits, syn, its, None, None, -1, 0, truth, m, counters, stream)
+            handle.call("ldpcb_select_flagged", syn, m, idx, cnt, stream)
+            nf = int(cnt.item())
+            if nf > 0:
+                llr_f, truth_f = e((nf, 128), torch.float32), e((nf, 4), torch.int32)
+                handle.call("ldpcb_gather_rows", llr, idx, cnt, nf, 128, llr_f, stream)
+                handle.call("ldpcb_gather_rows", truth.view(torch.float32), idx, cnt, nf, 4, truth_f.view(torch.float32), stream)
+                traj, bits_f = e((nf, rows, 128), torch.float32), e((nf, 4), torch.int32)
+                handle.call("ldpcb_nms_decode", llr_f, nf, iters, float(alpha), 1.0, 1.0, 0, bits_f, None, None, traj, stream)
+                metric = e((nf, 128), torch.float32)
+                handle.call("ldpcb_dia_fir", traj, nf, rows, taps, float(bias), metric, stream)
+                bm, ex, ts = e((nf, nb), torch.int64), e((nf,), torch.int32), e((nf,), torch.int64)
+                handle.call("ldpcb_osd_block_minima", metric, llr_f, nf, packed, int(packed.numel()), starts, nb, FLAGS_DL, bm, None, ex,
+                            truth_f, ts, None, stream)
+                handle.call("ldpcb_dl_window_policy", bm, ex, ts, nf, nb, int(win_width), W1, W2, float(soft_margin), acc_np, None, None, None,
+                            dl, stream)
+        both = np.concatenate([counters.cpu().numpy().view(np.uint64), dl.cpu().numpy().view(np.uint64), np.zeros(12, np.uint64)])
+        red = allreduce_counters(both[:16]), allreduce_counters(both[16:32])
+        tot += red[0]
+        tot_dl += red[1][:4]
+        done += n
+    t = Tallies(tot)
+    frames = max(t.frames, 1)
+    out = {"dl_success": int(tot_dl[0]), "dl_failure": int(tot_dl[1]), "windows_sum": int(tot_dl[2]), "complexity_sum": int(tot_dl[3]),
+           "fer_dl_stage": int(tot_dl[1]) / max(int(tot_dl[0] + tot_dl[1]), 1),
+           "fer_final": (int(tot_dl[1]) + t.nms_undetected) / frames,
+           "avg_teps": int(tot_dl[3]) / max(int(tot_dl[0] + tot_dl[1]), 1)}
+    return t, out
+
+
 def main(argv: Optional[Sequence[str]] = None) -> None:
     import torch
     import torch.distributed as dist

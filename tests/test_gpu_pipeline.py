@@ -200,3 +200,41 @@ def test_large_batch_properties(handle, code):
             x = x ^ (x >> s)
         par ^= x & 1
     assert int(par.sum()) == 0
+
+
+def test_dl_device_pipeline_equals_module_chain(handle, code):
+    """simulate.run_point_dl (all on device) against the drop-in module chain Decoding_model -> conv_bitwise ->
+    osd.sliding_osd on the same frames."""
+    from short_ldpc_decoding_osd_b200 import globalmap as GL
+    from short_ldpc_decoding_osd_b200 import ms_test, nn_net, nn_testing, simulate
+    from short_ldpc_decoding_osd_b200 import ordered_statistics_decoding as OSD
+
+    for k, v in dict(code_parameters=code, selected_decoder_type="NMS-1", num_iterations=12, threshold_sum=2, segment_num=6, soft_margin=0.9,
+                     decoding_length=30, sliding_win_width=5).items():
+        GL.set_map(k, v)
+    osd = OSD.osd(code)
+    path = nn_testing.filter_order_patterns(nn_testing.convention_segment_path())
+    tep_info = nn_testing.generate_teps(osd, path)
+    rng = np.random.default_rng(3)
+    taps = (np.full(13, 1 / 13) + 0.03 * rng.normal(size=13)).astype(np.float32)
+    net = nn_net.Predict_outlier_light(5, W1=np.eye(6, dtype=np.float32), W2=np.array([[0, -0.5], [0, 0.5], [0, 0], [0, 0], [0, 0], [0, 0.15]], np.float32))
+    B, seed = 6000, 77
+    t, out = simulate.run_point_dl(handle, 2.5, B, tep_info, taps, 0.05, net.W1, net.W2, seed=seed, chunk=4096)
+    # module chain on the same Philox frames
+    yd = empty((B, 128), torch.float32)
+    td = empty((B, 4), torch.int32)
+    handle.call("ldpcb_gen_frames", seed, 0, B, 2.5, yd, td, None)
+    sync()
+    y = yd.cpu().numpy()
+    lab = _lib.unpack_bits(td.cpu().numpy().view(np.uint32)).astype(np.int64)
+    model = ms_test.Decoding_model()
+    fer, ber, und, buffer = model(y, lab)
+    assert t.frames == B and t.nms_frame_err == round(fer * B) and t.nms_undetected == und
+    rows = np.stack(buffer[0])
+    labs = np.stack(buffer[1])
+    nn = nn_net.conv_bitwise()
+    nn.set_taps(taps, 0.05)
+    squashed, inputs0, labels0 = nn.preprocessing_inputs((rows, labs))
+    s, f, w, c = osd.sliding_osd(net, rows, nn(squashed), labels0, tep_info)
+    assert (out["dl_success"], out["dl_failure"], out["windows_sum"], out["complexity_sum"]) == (s, f, w, c)
+    assert s + f == t.nms_detected and out["fer_final"] == (f + und) / B
