@@ -70,7 +70,8 @@ class LdpcB200Error(RuntimeError):
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    """In-tree library, or the prebuilt one LDPCB_B200_LIB points at."""
+    return os.environ.get("LDPCB_B200_LIB") or _build.LIB_PATH
 
 
 def load(build_if_missing: bool = True) -> C.CDLL:

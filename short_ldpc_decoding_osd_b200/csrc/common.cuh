@@ -55,7 +55,11 @@ struct TepTable {
     std::vector<uint32_t> host;
     int n = 0;
     int maxw = 0;
+    // order 2 only: inverse of the enumeration, [i*64+j] (i<j) -> index of the pair TEP, [4096+i] -> index of the
+    // single TEP {i}, [4096+64] -> index of the empty TEP (the tensor-core pair sweep visits TEPs in its own order)
+    uint16_t* pair_dev = nullptr;
 };
+constexpr int OSD_PAIR_TABLE = 64 * 64 + 65;
 
 struct Workspace {
     char* buf = nullptr;
@@ -127,6 +131,7 @@ struct OsdArgs {
     const uint32_t* teps;
     int n_teps;
     int maxw;
+    const uint16_t* pair_index;  // optional (full order-2 tables): selects the tensor-core pair sweep
     const int32_t* block_start;  // NULL => one block [0,n_teps)
     int n_blocks;
     int flags;

@@ -109,6 +109,18 @@ int build_tep_tables(ldpcb_handle* h) {
             padded.resize(t.n + 128, 0xFFFFFFFFu);
             LDPCB_CUDA(h, cudaMalloc(&t.dev, sizeof(uint32_t) * padded.size()));
             LDPCB_CUDA(h, cudaMemcpy(t.dev, padded.data(), sizeof(uint32_t) * padded.size(), cudaMemcpyHostToDevice));
+            if (order == 2) {
+                std::vector<uint16_t> inv(OSD_PAIR_TABLE, 0xFFFFu);
+                for (int i = 0; i < t.n; ++i) {
+                    const uint32_t v = t.host[i];
+                    const unsigned a = v & 0xFFu, b = (v >> 8) & 0xFFu;
+                    if (a >= (unsigned)K) inv[K * K + K] = (uint16_t)i;
+                    else if (b >= (unsigned)K) inv[K * K + a] = (uint16_t)i;
+                    else inv[a * K + b] = (uint16_t)i;
+                }
+                LDPCB_CUDA(h, cudaMalloc(&t.pair_dev, sizeof(uint16_t) * inv.size()));
+                LDPCB_CUDA(h, cudaMemcpy(t.pair_dev, inv.data(), sizeof(uint16_t) * inv.size(), cudaMemcpyHostToDevice));
+            }
         }
     }
     return LDPCB_OK;
@@ -363,8 +375,10 @@ void ldpcb_destroy(ldpcb_t* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (int o = 0; o < 4; ++o)
-        for (int kd = 0; kd < 2; ++kd)
+        for (int kd = 0; kd < 2; ++kd) {
             if (h->tep[o][kd].dev) cudaFree(h->tep[o][kd].dev);
+            if (h->tep[o][kd].pair_dev) cudaFree(h->tep[o][kd].pair_dev);
+        }
     for (int i = 0; i < NUM_WS; ++i)
         if (h->ws[i].buf) cudaFree(h->ws[i].buf);
     for (int i = 0; i < 3; ++i) {

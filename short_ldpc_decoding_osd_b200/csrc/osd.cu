@@ -67,8 +67,57 @@ __device__ __forceinline__ long long score64(const OsdSmem& S, const FrameSm& G,
     return s;
 }
 
-template <int MAXW, bool BLOCKS>
-__global__ void __launch_bounds__(OSD_THREADS) osd_kernel(OsdArgs a, const uint64_t* __restrict__ gcol) {
+// ---- tensor-core pair sweep (full order-2 lists) ------------------------------------------------------------------
+// With u_i = d0 ^ P'_i the truncated score of the pair TEP {i, j} is
+//     S(i,j) = R_i + C_j - 2 * M[i][j],   R_i = base + qd_i + W(u_i)  (= score of the single TEP {i}),
+//     C_j = qd_j + W(P'_j),               M[i][j] = sum_l w_l * u_i[l] * P'_j[l]
+// (W(x ^ y) = W(x) + W(y) - 2 W(x & y) for a weighted popcount W).  M is a 64x64x64 integer matrix product per
+// frame: A[i][l] = w_l masked by bit l of u_i, split into two byte planes (w < 2^16), B[l][j] = bit l of P'_j, both
+// u8, accumulated in s32 by mma.sync m16n8k32 (IMMA.16832.U8.U8).  Only the 20 of the 32 16x8 tiles that contain a
+// pair i < j are computed, five per warp.  The 129 values R, C and the empty TEP's score come from the owner warp's
+// 5-bit shuffle tables.  Scores are packed as (S << 5) | code (code = tile and element, or a single / the empty
+// TEP), so a thread tracks its minimum and second minimum with three integer min/max per element; the candidates
+// within the truncation window of the CTA-wide minimum are re-scored exactly as in the generic sweep.
+constexpr int PAIR_SH = 38;  // w = floor(q / 2^38) < 2^16: two byte planes; window = 72 * 2^38 ~ 2^-9 of the largest |y|
+constexpr int PAIR_CODE_SINGLE = 28, PAIR_CODE_EMPTY = 30;
+__constant__ unsigned char c_pair_tiles[OSD_FPB][5][2] = {  // [warp][turn] -> (16-row block of i, 8-column block of j)
+    {{0, 0}, {0, 1}, {0, 2}, {0, 3}, {0, 4}},
+    {{0, 5}, {0, 6}, {0, 7}, {1, 2}, {1, 3}},
+    {{1, 4}, {1, 5}, {1, 6}, {1, 7}, {2, 4}},
+    {{2, 5}, {2, 6}, {2, 7}, {3, 6}, {3, 7}}};
+
+__device__ __forceinline__ void imma_u8(int (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// four bits -> four bytes of 0/1 (bit k of the nibble in byte k)
+__device__ __forceinline__ unsigned spread4(unsigned word, int sh) { return (((word >> sh) & 0xFu) * 0x00204081u) & 0x01010101u; }
+// weighted popcount of D through the thirteen 5-bit tables held one entry per lane
+__device__ __forceinline__ int wpop_shfl(const int (&tb)[13], unsigned long long D) {
+    const unsigned lo = (unsigned)D, hi = (unsigned)(D >> 32);
+    int s = __shfl_sync(0xffffffffu, tb[0], lo);  // the source lane is taken modulo 32
+    s += __shfl_sync(0xffffffffu, tb[1], lo >> 5);
+    s += __shfl_sync(0xffffffffu, tb[2], lo >> 10);
+    s += __shfl_sync(0xffffffffu, tb[3], lo >> 15);
+    s += __shfl_sync(0xffffffffu, tb[4], lo >> 20);
+    s += __shfl_sync(0xffffffffu, tb[5], lo >> 25);
+    s += __shfl_sync(0xffffffffu, tb[6], (unsigned)(D >> 30));
+    s += __shfl_sync(0xffffffffu, tb[7], hi >> 3);
+    s += __shfl_sync(0xffffffffu, tb[8], hi >> 8);
+    s += __shfl_sync(0xffffffffu, tb[9], hi >> 13);
+    s += __shfl_sync(0xffffffffu, tb[10], hi >> 18);
+    s += __shfl_sync(0xffffffffu, tb[11], hi >> 23);
+    s += __shfl_sync(0xffffffffu, tb[12], hi >> 28);
+    return s;
+}
+__device__ __forceinline__ void track2(int& s0, int& s1, int p) {
+    s1 = min(s1, max(p, s0));
+    s0 = min(s0, p);
+}
+
+template <int MAXW, bool BLOCKS, bool PAIR>
+__global__ void __launch_bounds__(OSD_THREADS, PAIR ? 6 : 6) osd_kernel(OsdArgs a, const uint64_t* __restrict__ gcol) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     OsdSmem& S = *reinterpret_cast<OsdSmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -84,30 +133,156 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_kernel(OsdArgs a, const uint6
         const bool active = f < nframes;
         const int64_t row = active ? (a.idx ? (int64_t)a.idx[f] : f) : 0;
         Prep P = {};
-        if (active) P = prepare_frame<BLOCKS>(a, F, gcol, row, f, lane, ties_high, disc_from_score);
+        if (active) P = prepare_frame<BLOCKS, PAIR ? PAIR_SH : 30>(a, F, gcol, row, f, lane, ties_high, disc_from_score);
         const unsigned char* pm = P.pm;
         const unsigned long long* myprow = P.myprow;
         const unsigned long long hd_lrb = P.hd_lrb, ho_mrb = P.ho_mrb, d0 = P.d0;
         const int E = P.E;
         // ---- 5./6. sweep: the four warps take the prepared frames in turn -------------------------------------
+        int sp0 = 0x7fffffff, sp1 = 0x7fffffff, spz = 0x7fffffff;  // pair sweep: packed scores of this lane's single TEPs and of the empty TEP
         if (!BLOCKS && active) {
             if (lane == 0) { S.cand_n[warp] = 0; S.cand_ovf[warp] = 0; }
             __syncwarp();
             // 5-bit chunk tables of the 32-bit LRB weights: tabs[j][e] = sum of w32[5j+i] over the set bits i of e
+            int tb[13];
 #pragma unroll
             for (int j = 0; j < 13; ++j) {
                 int v = 0;
 #pragma unroll
                 for (int i = 0; i < 5; ++i)
                     if (5 * j + i < 64) v += ((lane >> i) & 1) ? (int)F.w32[5 * j + i] : 0;
-                S.tabs[warp][j][lane] = v;
+                tb[j] = v;
+                if (!PAIR) S.tabs[warp][j][lane] = v;
+            }
+            if (PAIR) {
+                const int qa = F.qd32[lane], qb = F.qd32[lane + 32], b32 = F.base32;
+                const int z = b32 + wpop_shfl(tb, d0);
+                const int r0 = b32 + qa + wpop_shfl(tb, d0 ^ myprow[0]);
+                const int r1 = b32 + qb + wpop_shfl(tb, d0 ^ myprow[1]);
+                const int c0 = qa + wpop_shfl(tb, myprow[0]);
+                const int c1 = qb + wpop_shfl(tb, myprow[1]);
+                const unsigned wa = F.w32[lane], wb = F.w32[lane + 32];
+                __syncwarp();  // every lane is done with yo/ys: reuse them
+                int* RC = reinterpret_cast<int*>(F.yo);
+                RC[lane] = r0 << 5; RC[lane + 32] = r1 << 5;
+                RC[64 + lane] = c0 << 5; RC[96 + lane] = c1 << 5;
+                unsigned char* wq = reinterpret_cast<unsigned char*>(F.ys);  // [plane][LRB position]
+                wq[lane] = (unsigned char)(wa & 0xffu); wq[lane + 32] = (unsigned char)(wb & 0xffu);
+                wq[64 + lane] = (unsigned char)(wa >> 8); wq[96 + lane] = (unsigned char)(wb >> 8);
+                sp0 = (r0 << 5) | PAIR_CODE_SINGLE;
+                sp1 = (r1 << 5) | (PAIR_CODE_SINGLE + 1);
+                spz = (z << 5) | PAIR_CODE_EMPTY;
             }
         }
         const int nfr = (int)((nframes - f0) < OSD_FPB ? (nframes - f0) : OSD_FPB);
         for (int w = 0; w < nfr; ++w) {
             const FrameSm& G = S.fr[w];
             __syncthreads();  // (A) frame w prepared; reduction slots and LUT free
-            if (!BLOCKS) {
+            if (PAIR) {
+                const int g = lane >> 2, t = lane & 3;
+                const unsigned* wqw = reinterpret_cast<const unsigned*>(G.ys);
+                const int* RC = reinterpret_cast<const int*>(G.yo);
+                unsigned wr[2][2][2];  // [plane][32-bit half of the LRB][16-bit half]: the four weight bytes this thread's k columns need
+#pragma unroll
+                for (int p = 0; p < 2; ++p)
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) wr[p][kk][hh] = wqw[16 * p + 8 * kk + 4 * hh + t];
+                const unsigned long long gd0 = G.d0;
+                int s0 = 0x7fffffff, s1 = 0x7fffffff;
+                if (warp == w) {  // the owner warp brings the singles and the empty TEP
+                    track2(s0, s1, sp0);
+                    track2(s0, s1, sp1);
+                    if (lane == 0) track2(s0, s1, spz);
+                }
+                const int vb = g - 2 * t;  // i - j of element 0 in a tile on the diagonal
+                unsigned afr[2][2][4];     // [k half][plane][fragment register]
+                int rr[2] = {0, 0};
+                int cur_mi = -1;
+#pragma unroll
+                for (int tt = 0; tt < 5; ++tt) {
+                    const int mi = c_pair_tiles[warp][tt][0], nj = c_pair_tiles[warp][tt][1];
+                    if (mi != cur_mi) {  // warp-uniform: masked weights of rows 16mi+g and +8
+                        cur_mi = mi;
+                        const int i0 = 16 * mi + g;
+                        const unsigned long long u0 = gd0 ^ G.prow[i0], u1 = gd0 ^ G.prow[i0 + 8];
+                        rr[0] = RC[i0];
+                        rr[1] = RC[i0 + 8];
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const unsigned w0 = kk ? (unsigned)(u0 >> 32) : (unsigned)u0;
+                            const unsigned w1 = kk ? (unsigned)(u1 >> 32) : (unsigned)u1;
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const unsigned m0 = spread4(w0, 4 * t + 16 * hh) * 0xFFu;
+                                const unsigned m1 = spread4(w1, 4 * t + 16 * hh) * 0xFFu;
+#pragma unroll
+                                for (int p = 0; p < 2; ++p) {
+                                    afr[kk][p][2 * hh] = wr[p][kk][hh] & m0;
+                                    afr[kk][p][2 * hh + 1] = wr[p][kk][hh] & m1;
+                                }
+                            }
+                        }
+                    }
+                    const unsigned long long cj = G.prow[8 * nj + g];
+                    unsigned bfr[2][2];
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh)
+                            bfr[kk][hh] = spread4(kk ? (unsigned)(cj >> 32) : (unsigned)cj, 4 * t + 16 * hh);
+                    int acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+                        for (int p = 0; p < 2; ++p) imma_u8(acc[p], afr[kk][p], bfr[kk]);
+                    const int2 cc = *reinterpret_cast<const int2*>(RC + 64 + 8 * nj + 2 * t);
+                    const int dlt = 8 * nj - 16 * mi;  // < 16: the tile straddles the diagonal
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int rs = e >> 1, cs = e & 1;
+                        const int rc = rr[rs] + (cs ? cc.y : cc.x) + ((tt << 2) | e);
+                        int p = rc - 64 * acc[0][e] - 16384 * acc[1][e];  // ((R + C - 2M) << 5) | code
+                        if (dlt < 16 && vb + 8 * rs - cs >= dlt) p = 0x7fffffff;  // i >= j
+                        track2(s0, s1, p);
+                    }
+                }
+                int m = s0;
+#pragma unroll
+                for (int x = 16; x; x >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, x));
+                if (lane == 0) S.red32[warp] = m;
+                __syncthreads();  // (B)
+                m = min(min(S.red32[0], S.red32[1]), min(S.red32[2], S.red32[3]));
+                const int lim = (((m >> 5) + OSD_WIN) << 5) | 31;
+                if (s0 <= lim) {
+                    const int code = s0 & 31;
+                    int pi;
+                    if (code < PAIR_CODE_SINGLE) {
+                        const int tt = code >> 2, e = code & 3;
+                        const int i = 16 * c_pair_tiles[warp][tt][0] + g + 8 * (e >> 1), j = 8 * c_pair_tiles[warp][tt][1] + 2 * t + (e & 1);
+                        pi = i * K + j;
+                    } else {
+                        pi = K * K + (code == PAIR_CODE_EMPTY ? K : lane + 32 * (code - PAIR_CODE_SINGLE));
+                    }
+                    const int p = atomicAdd(&S.cand_n[w], 1);
+                    if (p < OSD_CAND_CAP) S.cand_i[w][p] = (int)a.pair_index[pi];
+                }
+                if (s1 <= lim) S.cand_ovf[w] = 1;  // a second candidate of this thread: take the exact path
+                __syncthreads();  // (C)
+                if (S.cand_ovf[w] || S.cand_n[w] > OSD_CAND_CAP) {
+                    build_lut64(S, G, tid);
+                    __syncthreads();
+                    long long bs = 0x7fffffffffffffffll;
+                    int bi = 0x7fffffff;
+                    for (int i = tid; i < a.n_teps; i += OSD_THREADS) {
+                        const long long s = score64<MAXW>(S, G, __ldg(a.teps + i));
+                        if (s < bs) { bs = s; bi = i; }
+                    }
+                    warp_argmin(bs, bi);
+                    if (lane == 0) { S.red_s[w][warp] = bs; S.red_i[w][warp] = bi; }
+                }
+            } else if (!BLOCKS) {
                 // Fast sweep on 32-bit truncated scores S32 = sum floor(term / 2^30): the 64 LRB weights are folded
                 // into thirteen 32-entry tables (5 bits of D each) that live in registers, one entry per lane, and
                 // are looked up with warp shuffles -- no shared-memory bank conflicts.  The exact score satisfies
@@ -483,9 +658,9 @@ int launch_osd_fs(ldpcb_handle* h, const OsdArgs& a, const FsParams& fp, cudaStr
     return LDPCB_OK;
 }
 
-template <int MAXW, bool BLOCKS>
+template <int MAXW, bool BLOCKS, bool PAIR = false>
 static int launch_variant(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st) {
-    auto kern = osd_kernel<MAXW, BLOCKS>;
+    auto kern = osd_kernel<MAXW, BLOCKS, PAIR>;
     const int smem = (int)sizeof(OsdSmem);
     static thread_local int occ_cache[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int& occ = occ_cache[h->device & 7];
@@ -508,7 +683,9 @@ int launch_osd(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st) {
     const bool blocks = a.block_start != nullptr;
     switch (a.maxw) {
         case 1: return blocks ? launch_variant<1, true>(h, a, st) : launch_variant<1, false>(h, a, st);
-        case 2: return blocks ? launch_variant<2, true>(h, a, st) : launch_variant<2, false>(h, a, st);
+        case 2:
+            if (blocks) return launch_variant<2, true>(h, a, st);
+            return (a.pair_index && a.n_teps == 2081) ? launch_variant<2, false, true>(h, a, st) : launch_variant<2, false>(h, a, st);
         case 3: return blocks ? launch_variant<3, true>(h, a, st) : launch_variant<3, false>(h, a, st);
         default: return blocks ? launch_variant<4, true>(h, a, st) : launch_variant<4, false>(h, a, st);
     }
@@ -538,7 +715,7 @@ extern "C" int ldpcb_osd_decode(ldpcb_t* h, const float* order_llr_dev, const fl
     const TepTable& t = h->tep[order][tep_order];
     OsdArgs a = {};
     a.order_llr = order_llr_dev; a.score_llr = score_llr_dev; a.B = B;
-    a.teps = t.dev; a.n_teps = t.n; a.maxw = t.maxw; a.flags = flags;
+    a.teps = t.dev; a.n_teps = t.n; a.maxw = t.maxw; a.pair_index = t.pair_dev; a.flags = flags;
     a.cw_bits = cw_bits_dev; a.best_tep = best_tep_dev; a.best_score_q = best_score_q_dev;
     a.score_exp = score_exp_dev; a.perm = perm_dev; a.redG = redG_dev;
     return launch_osd(h, a, (cudaStream_t)stream);

@@ -13,14 +13,14 @@ struct __align__(16) FrameSm {
     unsigned long long prow[66];  // P' rows by MRB position, [64] = 0 for padded TEP slots
     long long qd[66];             // signed score delta of flipping MRB position t, [64] = 0
     unsigned long long qlrb[64];  // q of the LRB positions          (qd..qlrb are reused as cols[128])
-    float yo[N];                  // ordering metric (original positions)
-    float ys[N];                  // scoring metric
+    float yo[N];                  // ordering metric (original positions); pair sweep: reused as R32[64], C32[64]
+    float ys[N];                  // scoring metric; pair sweep: reused as the two byte planes of the weights
     unsigned long long d0;        // order-0 discrepancy on the LRB
     long long base;               // order-0 discrepancy weight on the MRB
     unsigned long long d0m;       // order-0 discrepancy bits on the MRB (0 when both metrics agree)
-    unsigned w32[64];             // floor(q_lrb / 2^30): 32-bit weights of the fast sweep
-    int qd32[66];                 // floor(qd / 2^30), [64] = 0
-    int base32;                   // floor(base / 2^30)
+    unsigned w32[64];             // floor(q_lrb / 2^SH): 32-bit weights of the fast sweeps (SH = 30, pair sweep 38)
+    int qd32[66];                 // floor(qd / 2^SH), [64] = 0
+    int base32;                   // floor(base / 2^SH)
     int pad32;
     unsigned char pi1[N];         // sorted position -> original index
     unsigned char pos[N];         // permuted position (MRB then LRB) -> sorted position
@@ -154,7 +154,8 @@ struct Prep {
 };
 
 // Steps 1-4 for one frame by one warp; fills F (prow, qd, qlrb, d0, base) and returns the registers above.
-template <bool TRUTH>
+// SH: truncation of the fast sweeps' 32-bit weights, w32 = floor(q / 2^SH)
+template <bool TRUTH, int SH = 30>
 __device__ __forceinline__ Prep prepare_frame(const OsdArgs& a, FrameSm& F, const uint64_t* __restrict__ gcol, int64_t row,
                                               int64_t f, int lane, bool ties_high, bool disc_from_score) {
     unsigned long long* cols = reinterpret_cast<unsigned long long*>(F.qd);  // [128], dead before qd/qlrb are written
@@ -311,14 +312,14 @@ __device__ __forceinline__ Prep prepare_frame(const OsdArgs& a, FrameSm& F, cons
         const unsigned d0m = ho[k] ^ hd[k];
         const long long qdv = d0m ? -q[k] : q[k];
         F.qd[lane + 32 * k] = qdv;
-        F.qd32[lane + 32 * k] = (int)(qdv >> 30);
+        F.qd32[lane + 32 * k] = (int)(qdv >> SH);
         base += d0m ? q[k] : 0ll;
     }
     base = warp_sum_ll(base);
     F.qlrb[lane] = (unsigned long long)q[2];
     F.qlrb[lane + 32] = (unsigned long long)q[3];
-    F.w32[lane] = (unsigned)(q[2] >> 30);
-    F.w32[lane + 32] = (unsigned)(q[3] >> 30);
+    F.w32[lane] = (unsigned)(q[2] >> SH);
+    F.w32[lane + 32] = (unsigned)(q[3] >> SH);
     F.prow[lane] = myprow[0];
     F.prow[lane + 32] = myprow[1];
     unsigned long long c0 = (ho[0] ? myprow[0] : 0ull) ^ (ho[1] ? myprow[1] : 0ull);
@@ -327,7 +328,7 @@ __device__ __forceinline__ Prep prepare_frame(const OsdArgs& a, FrameSm& F, cons
     ho_mrb = (unsigned long long)__ballot_sync(0xffffffffu, ho[0]) | ((unsigned long long)__ballot_sync(0xffffffffu, ho[1]) << 32);
     const unsigned long long hd_mrb_out = (unsigned long long)__ballot_sync(0xffffffffu, hd[0]) | ((unsigned long long)__ballot_sync(0xffffffffu, hd[1]) << 32);
     d0 = c0 ^ hd_lrb;
-    if (lane == 0) { F.d0 = d0; F.base = base; F.d0m = ho_mrb ^ hd_mrb_out; F.prow[64] = 0ull; F.qd[64] = 0ll; F.qd32[64] = 0; F.base32 = (int)(base >> 30); }  // [64]: padded TEP slots (qd aliases cols until here)
+    if (lane == 0) { F.d0 = d0; F.base = base; F.d0m = ho_mrb ^ hd_mrb_out; F.prow[64] = 0ull; F.qd[64] = 0ll; F.qd32[64] = 0; F.base32 = (int)(base >> SH); }  // [64]: padded TEP slots (qd aliases cols until here)
     if (TRUTH && a.truth_bits && a.truth_score_q) {
         long long ts = 0;
 #pragma unroll

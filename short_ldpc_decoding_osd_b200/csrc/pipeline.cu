@@ -77,7 +77,7 @@ static int decode_on_device(ldpcb_handle* h, const DecodeWs& w, const float* llr
         const TepTable& t = h->tep[p.osd_order][p.tep_order];
         OsdArgs a = {};
         a.order_llr = llr; a.score_llr = llr; a.idx = w.idx; a.count = w.count; a.B = B;
-        a.teps = t.dev; a.n_teps = t.n; a.maxw = t.maxw; a.flags = 0;
+        a.teps = t.dev; a.n_teps = t.n; a.maxw = t.maxw; a.pair_index = t.pair_dev; a.flags = 0;
         a.cw_bits = final_bits; a.best_tep = best_tep;
         s = launch_osd(h, a, st);
         if (s != LDPCB_OK) return s;
@@ -233,7 +233,7 @@ extern "C" int ldpcb_osd_decode_host(ldpcb_t* h, const float* order_llr_host, co
         LDPCB_CUDA(h, cudaMemcpyAsync(ol, order_llr_host + b0 * N, sizeof(float) * nb * N, cudaMemcpyHostToDevice, st));
         if (!same) LDPCB_CUDA(h, cudaMemcpyAsync(sl, score_llr_host + b0 * N, sizeof(float) * nb * N, cudaMemcpyHostToDevice, st));
         OsdArgs a = {};
-        a.order_llr = ol; a.score_llr = same ? ol : sl; a.B = nb; a.teps = t.dev; a.n_teps = t.n; a.maxw = t.maxw; a.flags = flags;
+        a.order_llr = ol; a.score_llr = same ? ol : sl; a.B = nb; a.teps = t.dev; a.n_teps = t.n; a.maxw = t.maxw; a.pair_index = t.pair_dev; a.flags = flags;
         a.cw_bits = bits; a.best_tep = bt; a.best_score_q = bq; a.score_exp = ex;
         a.perm = perm_host ? pm : nullptr; a.redG = redG_host ? rg : nullptr;
         if ((s = launch_osd(h, a, st)) != LDPCB_OK) return s;
