@@ -32,7 +32,7 @@
 namespace ldpcb {
 
 constexpr int OSD_WIN = 72;       // >= 64 LRB terms + 4 MRB terms + 1 base term
-constexpr int OSD_CAND_CAP = 32;
+constexpr int OSD_CAND_CAP = 16;
 
 // lut[b][x] = sum of q_lrb[8b+i] over the set bits i of x; thread: table b, low nibble fixed
 __device__ __forceinline__ void build_lut64(OsdSmem& S, const FrameSm& G, int tid) {
@@ -425,14 +425,14 @@ __global__ void __launch_bounds__(OSD_THREADS, PAIR ? 6 : 6) osd_kernel(OsdArgs 
                 }
                 const unsigned long long c_lrb = D ^ hd_lrb;
                 const unsigned long long c_mrb = ho_mrb ^ flip;
-                F.tmp[pm[0]] = (unsigned char)((c_mrb >> lane) & 1ull);
-                F.tmp[pm[1]] = (unsigned char)((c_mrb >> (lane + 32)) & 1ull);
-                F.tmp[pm[2]] = (unsigned char)((c_lrb >> lane) & 1ull);
-                F.tmp[pm[3]] = (unsigned char)((c_lrb >> (lane + 32)) & 1ull);
+                F.pos[pm[0]] = (unsigned char)((c_mrb >> lane) & 1ull);
+                F.pos[pm[1]] = (unsigned char)((c_mrb >> (lane + 32)) & 1ull);
+                F.pos[pm[2]] = (unsigned char)((c_lrb >> lane) & 1ull);
+                F.pos[pm[3]] = (unsigned char)((c_lrb >> (lane + 32)) & 1ull);
                 __syncwarp();
                 unsigned wout[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) wout[k] = __ballot_sync(0xffffffffu, F.tmp[lane + 32 * k]);
+                for (int k = 0; k < 4; ++k) wout[k] = __ballot_sync(0xffffffffu, F.pos[lane + 32 * k]);
                 const int64_t orow = a.idx ? row : f;
                 if (lane < 4 && a.cw_bits) {
                     const unsigned wv = lane == 0 ? wout[0] : lane == 1 ? wout[1] : lane == 2 ? wout[2] : wout[3];
@@ -610,14 +610,14 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_fs_kernel(OsdArgs a, FsParams
             }
             const unsigned long long c_lrb = D ^ P.hd_lrb;
             const unsigned long long c_mrb = P.ho_mrb ^ flip;
-            F.tmp[P.pm[0]] = (unsigned char)((c_mrb >> lane) & 1ull);
-            F.tmp[P.pm[1]] = (unsigned char)((c_mrb >> (lane + 32)) & 1ull);
-            F.tmp[P.pm[2]] = (unsigned char)((c_lrb >> lane) & 1ull);
-            F.tmp[P.pm[3]] = (unsigned char)((c_lrb >> (lane + 32)) & 1ull);
+            F.pos[P.pm[0]] = (unsigned char)((c_mrb >> lane) & 1ull);
+            F.pos[P.pm[1]] = (unsigned char)((c_mrb >> (lane + 32)) & 1ull);
+            F.pos[P.pm[2]] = (unsigned char)((c_lrb >> lane) & 1ull);
+            F.pos[P.pm[3]] = (unsigned char)((c_lrb >> (lane + 32)) & 1ull);
             __syncwarp();
             unsigned wout[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) wout[k] = __ballot_sync(0xffffffffu, F.tmp[lane + 32 * k]);
+            for (int k = 0; k < 4; ++k) wout[k] = __ballot_sync(0xffffffffu, F.pos[lane + 32 * k]);
             const int64_t orow = a.idx ? row : f;
             if (lane < 4 && a.cw_bits) {
                 const unsigned wv = lane == 0 ? wout[0] : lane == 1 ? wout[1] : lane == 2 ? wout[2] : wout[3];
@@ -661,7 +661,8 @@ int launch_osd_fs(ldpcb_handle* h, const OsdArgs& a, const FsParams& fp, cudaStr
 template <int MAXW, bool BLOCKS, bool PAIR = false>
 static int launch_variant(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st) {
     auto kern = osd_kernel<MAXW, BLOCKS, PAIR>;
-    const int smem = (int)sizeof(OsdSmem);
+    static_assert(offsetof(OsdSmem, tabs) == OSD_SMEM_NO_TABS, "OsdSmem layout changed");
+    const int smem = PAIR ? OSD_SMEM_NO_TABS : (int)sizeof(OsdSmem);
     static thread_local int occ_cache[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int& occ = occ_cache[h->device & 7];
     if (occ == 0) {

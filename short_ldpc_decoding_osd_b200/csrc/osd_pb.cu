@@ -201,14 +201,14 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_pb_kernel(OsdArgs a, PbParams
         const unsigned long long c_lrb = opt_D ^ P.hd_lrb;
         const unsigned long long c_mrb = P.ho_mrb ^ opt_flip;
         __syncwarp();
-        F.tmp[P.pm[0]] = (unsigned char)((c_mrb >> lane) & 1ull);
-        F.tmp[P.pm[1]] = (unsigned char)((c_mrb >> (lane + 32)) & 1ull);
-        F.tmp[P.pm[2]] = (unsigned char)((c_lrb >> lane) & 1ull);
-        F.tmp[P.pm[3]] = (unsigned char)((c_lrb >> (lane + 32)) & 1ull);
+        F.pos[P.pm[0]] = (unsigned char)((c_mrb >> lane) & 1ull);
+        F.pos[P.pm[1]] = (unsigned char)((c_mrb >> (lane + 32)) & 1ull);
+        F.pos[P.pm[2]] = (unsigned char)((c_lrb >> lane) & 1ull);
+        F.pos[P.pm[3]] = (unsigned char)((c_lrb >> (lane + 32)) & 1ull);
         __syncwarp();
         unsigned wout[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) wout[k] = __ballot_sync(0xffffffffu, F.tmp[lane + 32 * k]);
+        for (int k = 0; k < 4; ++k) wout[k] = __ballot_sync(0xffffffffu, F.pos[lane + 32 * k]);
         const int64_t orow = a.idx ? row : f;
         if (lane < 4 && a.cw_bits) {
             const unsigned wv = lane == 0 ? wout[0] : lane == 1 ? wout[1] : lane == 2 ? wout[2] : wout[3];

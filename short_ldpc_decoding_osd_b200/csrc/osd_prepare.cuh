@@ -23,9 +23,9 @@ struct __align__(16) FrameSm {
     int base32;                   // floor(base / 2^SH)
     int pad32;
     unsigned char pi1[N];         // sorted position -> original index
-    unsigned char pos[N];         // permuted position (MRB then LRB) -> sorted position
+    unsigned char pos[N];         // permuted position (MRB then LRB) -> sorted position; dead after prepare and reused
+                                  // as the scatter buffer of the output step
     unsigned char prow_of[K];     // pivot row of MRB position t
-    unsigned char tmp[N];
 };
 
 struct __align__(16) OsdSmem {
@@ -36,12 +36,15 @@ struct __align__(16) OsdSmem {
     int red32[OSD_FPB];              // fast sweep: per-warp minima of the 32-bit scores
     int cand_n[OSD_FPB];             // fast sweep: candidates whose exact score can still be the minimum
     int cand_ovf[OSD_FPB];
-    int cand_i[OSD_FPB][32];
-    int tabs[OSD_FPB][13][32];       // fast sweep: 5-bit chunk tables of each frame (entry = lane)
+    int cand_i[OSD_FPB][16];
     int red_stop[OSD_FPB];           // FS: per-warp first stopping TEP index
     long long fs_score[OSD_FPB];     // FS results per frame
     int fs_opt[OSD_FPB], fs_num[OSD_FPB], fs_kind[OSD_FPB];
+    int tabs[OSD_FPB][13][32];       // fast sweep: 5-bit chunk tables of each frame (entry = lane); last member: the
+                                     // pair sweep keeps its tables in registers and is launched without this part
 };
+constexpr int OSD_SMEM_NO_TABS = 16384 + OSD_FPB * (int)sizeof(FrameSm) + 8 * OSD_FPB * OSD_FPB + 4 * OSD_FPB * OSD_FPB + 3 * 4 * OSD_FPB +
+                                 4 * OSD_FPB * 16 + 4 * OSD_FPB + 8 * OSD_FPB + 3 * 4 * OSD_FPB;
 
 __device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) {
     unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src);
@@ -83,6 +86,14 @@ __device__ __forceinline__ float score_abs(float y) {
     float a = fabsf(y);
     if (!(a == a)) a = 0.0f;
     return fminf(a, 3.402823466e38f);
+}
+
+// if (test & bit) { lo ^= xl; hi ^= xh; } as one LOP3-to-predicate and two predicated XORs (the compiler's own choice
+// for the C++ form is four selects and two XORs)
+__device__ __forceinline__ void xor_if_bit(unsigned& lo, unsigned& hi, unsigned test, unsigned bit, unsigned xl, unsigned xh) {
+    asm("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.u32 q, t, 0;\n\t@q xor.b32 %0, %0, %4;\n\t@q xor.b32 %1, %1, %5;\n\t}"
+        : "+r"(lo), "+r"(hi)
+        : "r"(test), "r"(bit), "r"(xl), "r"(xh));
 }
 
 // 32x32 bit-matrix transpose across the warp: in: lane i holds word x_i; out: bit j of lane i = bit i of x_j
@@ -217,49 +228,47 @@ __device__ __forceinline__ Prep prepare_frame(const OsdArgs& a, FrameSm& F, cons
         }
         {
             unsigned used_lo = 0u, used_hi = 0u;
-            int npiv = 0, nlrb = 0, c_next = N;
-            for (int l = 0; l < 32 && npiv < K; ++l) {
+            int npiv = 0, nlrb = 0, l = 0;
+            // once the basis is complete no row is free, so the remaining columns of a group of four fall through the
+            // "dependent" branch, which is what they are: the count is only tested once per group
+            for (; l < 32 && npiv < K; ++l) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (npiv < K) {
-                        const int c = 4 * l + k;
-                        const unsigned cl = __shfl_sync(0xffffffffu, clo[k], l);
-                        const unsigned ch = __shfl_sync(0xffffffffu, chi[k], l);
-                        const unsigned al = cl & ~used_lo, ah = ch & ~used_hi;
-                        if ((al | ah) == 0u) {  // dependent on more reliable columns
-                            if (lane == 0) F.pos[K + nlrb] = (unsigned char)c;
-                            ++nlrb;
-                        } else {
-                            int p;
-                            if (al != 0u) {  // pivot row in the low word (any unused row with a 1 gives the same basis)
-                                const unsigned bit = al & (0u - al);
-                                p = 31 - __clz(bit);
-                                used_lo |= bit;
-                                const unsigned ml = cl ^ bit;
-                                if ((ml | ch) != 0u) {  // an untouched unit column (information position of G) needs no row operation
+                    const int c = 4 * l + k;
+                    const unsigned cl = __shfl_sync(0xffffffffu, clo[k], l);
+                    const unsigned ch = __shfl_sync(0xffffffffu, chi[k], l);
+                    const unsigned al = cl & ~used_lo, ah = ch & ~used_hi;
+                    if ((al | ah) == 0u) {  // dependent on more reliable columns
+                        if (lane == 0) F.pos[K + nlrb] = (unsigned char)c;
+                        ++nlrb;
+                    } else {
+                        int p;
+                        if (al != 0u) {  // pivot row in the low word (any unused row with a 1 gives the same basis)
+                            const unsigned bit = al & (0u - al);
+                            p = 31 - __clz(bit);
+                            used_lo |= bit;
+                            const unsigned ml = cl ^ bit;
+                            if ((ml | ch) != 0u) {  // an untouched unit column (information position of G) needs no row operation
 #pragma unroll
-                                    for (int kk = 0; kk < 4; ++kk)
-                                        if (clo[kk] & bit) { clo[kk] ^= ml; chi[kk] ^= ch; }
-                                }
-                            } else {
-                                const unsigned bit = ah & (0u - ah);
-                                p = 63 - __clz(bit);
-                                used_hi |= bit;
-                                const unsigned mh = ch ^ bit;
-                                if ((cl | mh) != 0u) {
-#pragma unroll
-                                    for (int kk = 0; kk < 4; ++kk)
-                                        if (chi[kk] & bit) { clo[kk] ^= cl; chi[kk] ^= mh; }
-                                }
+                                for (int kk = 0; kk < 4; ++kk) xor_if_bit(clo[kk], chi[kk], clo[kk], bit, ml, ch);
                             }
-                            if (lane == 0) { F.pos[npiv] = (unsigned char)c; F.prow_of[npiv] = (unsigned char)p; }
-                            if (++npiv == K) c_next = c + 1;
+                        } else {
+                            const unsigned bit = ah & (0u - ah);
+                            p = 63 - __clz(bit);
+                            used_hi |= bit;
+                            const unsigned mh = ch ^ bit;
+                            if ((cl | mh) != 0u) {
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk) xor_if_bit(clo[kk], chi[kk], chi[kk], bit, cl, mh);
+                            }
                         }
+                        if (lane == 0) { F.pos[npiv] = (unsigned char)c; F.prow_of[npiv] = (unsigned char)p; }
+                        ++npiv;
                     }
                 }
             }
             // basis complete: every remaining position is LRB
-            for (int t = lane; c_next + t < N; t += 32) F.pos[K + nlrb + t] = (unsigned char)(c_next + t);
+            for (int t = 4 * l + lane; t < N; t += 32) F.pos[K + nlrb + t - 4 * l] = (unsigned char)t;
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) cols[4 * lane + k] = ((unsigned long long)chi[k] << 32) | clo[k];
