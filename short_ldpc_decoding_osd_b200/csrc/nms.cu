@@ -141,13 +141,17 @@ __global__ void __launch_bounds__(NMS_THREADS, 3) nms_kernel(NmsArgs a, const Nm
                 sx &= 0x80000000u;
                 const unsigned u1 = __float_as_uint(a1) ^ sx, u2 = __float_as_uint(a2) ^ sx;
                 const unsigned du = u1 - u2;
+                // select u1 where |x| > m1 (strict, ms_test.py:206) else u2 without a compare: |x| >= m1 always, so
+                // min(|x|, nextafter(m1)) is m1 or its successor, whose bit patterns differ by exactly one, and
+                // u = u2 + (bits(min) - bits(m1)) * du is one integer multiply-add on the FMA pipe (the ALU pipe is the busy one)
+                const unsigned m1b = __float_as_uint(m1);
+                const float m1p = __uint_as_float(m1b + 1u);
+                const unsigned kc = u2 - m1b * du;
 #pragma unroll
                 for (int e = 0; e < DC; ++e) {
-                    // select u1 where |x| > m1 (strict, ms_test.py:206) else u2, with the compare and the blend on the
-                    // FMA pipe (the ALU pipe is the busy one): m1 - |x| is negative exactly when |x| > m1
-                    const unsigned gt = __float_as_uint(__fsub_rn(m1, ax[e])) >> 31;
+                    const unsigned tb = __float_as_uint(fminf(ax[e], m1p));
                     unsigned u;
-                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(u) : "r"(gt), "r"(du), "r"(u2));
+                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(u) : "r"(tb), "r"(du), "r"(kc));
                     const float o = __uint_as_float(u ^ (__float_as_uint(x[e]) & 0x80000000u));
                     cvo[q][e] = o;
                     CV[REG8 ? (e * NMS_CV_STRIDE + rot[e] + lane + 32 * q) : cs[q][e]] = o;

@@ -93,6 +93,13 @@ __device__ __forceinline__ void imma_u8(int (&c)[4], const unsigned (&a)[4], con
 }
 // four bits -> four bytes of 0/1 (bit k of the nibble in byte k)
 __device__ __forceinline__ unsigned spread4(unsigned word, int sh) { return (((word >> sh) & 0xFu) * 0x00204081u) & 0x01010101u; }
+// four bits -> four bytes of 0x00/0xFF: the bits are moved to the byte sign positions and replicated by PRMT
+__device__ __forceinline__ unsigned mask4(unsigned word, int sh) {
+    const unsigned x = ((word >> sh) & 0xFu) * 0x10204080u;
+    unsigned r;
+    asm("prmt.b32 %0, %1, 0, 0xba98;" : "=r"(r) : "r"(x));  // selector nibble 8+k: replicate the sign of byte k
+    return r;
+}
 // weighted popcount of D through the thirteen 5-bit tables held one entry per lane
 __device__ __forceinline__ int wpop_shfl(const int (&tb)[13], unsigned long long D) {
     const unsigned lo = (unsigned)D, hi = (unsigned)(D >> 32);
@@ -145,14 +152,26 @@ __global__ void __launch_bounds__(OSD_THREADS, PAIR ? 6 : 6) osd_kernel(OsdArgs 
             __syncwarp();
             // 5-bit chunk tables of the 32-bit LRB weights: tabs[j][e] = sum of w32[5j+i] over the set bits i of e
             int tb[13];
+            {
+                unsigned lb[5];
 #pragma unroll
-            for (int j = 0; j < 13; ++j) {
-                int v = 0;
+                for (int i = 0; i < 5; ++i) lb[i] = (lane >> i) & 1u;
 #pragma unroll
-                for (int i = 0; i < 5; ++i)
-                    if (5 * j + i < 64) v += ((lane >> i) & 1) ? (int)F.w32[5 * j + i] : 0;
-                tb[j] = v;
-                if (!PAIR) S.tabs[warp][j][lane] = v;
+                for (int j = 0; j < 13; ++j) tb[j] = 0;
+#pragma unroll
+                for (int v4 = 0; v4 < 16; ++v4) {  // four weights per (broadcast) load, one multiply-add per term
+                    const uint4 wv = reinterpret_cast<const uint4*>(F.w32)[v4];
+                    const unsigned ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int pos = 4 * v4 + u;
+                        tb[pos / 5] += (int)(lb[pos % 5] * ww[u]);
+                    }
+                }
+                if (!PAIR) {
+#pragma unroll
+                    for (int j = 0; j < 13; ++j) S.tabs[warp][j][lane] = tb[j];
+                }
             }
             if (PAIR) {
                 const int qa = F.qd32[lane], qb = F.qd32[lane + 32], b32 = F.base32;
@@ -215,8 +234,8 @@ __global__ void __launch_bounds__(OSD_THREADS, PAIR ? 6 : 6) osd_kernel(OsdArgs 
                             const unsigned w1 = kk ? (unsigned)(u1 >> 32) : (unsigned)u1;
 #pragma unroll
                             for (int hh = 0; hh < 2; ++hh) {
-                                const unsigned m0 = spread4(w0, 4 * t + 16 * hh) * 0xFFu;
-                                const unsigned m1 = spread4(w1, 4 * t + 16 * hh) * 0xFFu;
+                                const unsigned m0 = mask4(w0, 4 * t + 16 * hh);
+                                const unsigned m1 = mask4(w1, 4 * t + 16 * hh);
 #pragma unroll
                                 for (int p = 0; p < 2; ++p) {
                                     afr[kk][p][2 * hh] = wr[p][kk][hh] & m0;
@@ -238,13 +257,14 @@ __global__ void __launch_bounds__(OSD_THREADS, PAIR ? 6 : 6) osd_kernel(OsdArgs 
 #pragma unroll
                         for (int p = 0; p < 2; ++p) imma_u8(acc[p], afr[kk][p], bfr[kk]);
                     const int2 cc = *reinterpret_cast<const int2*>(RC + 64 + 8 * nj + 2 * t);
-                    const int dlt = 8 * nj - 16 * mi;  // < 16: the tile straddles the diagonal
+                    const int dlt = 8 * nj - 16 * mi;
+                    const bool diag = dlt < 16;  // the tile straddles the diagonal (warp-uniform)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int rs = e >> 1, cs = e & 1;
                         const int rc = rr[rs] + (cs ? cc.y : cc.x) + ((tt << 2) | e);
                         int p = rc - 64 * acc[0][e] - 16384 * acc[1][e];  // ((R + C - 2M) << 5) | code
-                        if (dlt < 16 && vb + 8 * rs - cs >= dlt) p = 0x7fffffff;  // i >= j
+                        if (diag && vb + 8 * rs - cs >= dlt) p = 0x7fffffff;  // i >= j
                         track2(s0, s1, p);
                     }
                 }

@@ -13,12 +13,12 @@ struct __align__(16) FrameSm {
     unsigned long long prow[66];  // P' rows by MRB position, [64] = 0 for padded TEP slots
     long long qd[66];             // signed score delta of flipping MRB position t, [64] = 0
     unsigned long long qlrb[64];  // q of the LRB positions          (qd..qlrb are reused as cols[128])
+    unsigned w32[64];             // floor(q_lrb / 2^SH): 32-bit weights of the fast sweeps (SH = 30, pair sweep 38); 16-byte aligned
     float yo[N];                  // ordering metric (original positions); pair sweep: reused as R32[64], C32[64]
     float ys[N];                  // scoring metric; pair sweep: reused as the two byte planes of the weights
     unsigned long long d0;        // order-0 discrepancy on the LRB
     long long base;               // order-0 discrepancy weight on the MRB
     unsigned long long d0m;       // order-0 discrepancy bits on the MRB (0 when both metrics agree)
-    unsigned w32[64];             // floor(q_lrb / 2^SH): 32-bit weights of the fast sweeps (SH = 30, pair sweep 38)
     int qd32[66];                 // floor(qd / 2^SH), [64] = 0
     int base32;                   // floor(base / 2^SH)
     int pad32;
