@@ -43,7 +43,7 @@ def parse():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--frames", type=int, default=1 << 21, help="frames per GPU per step")
-    p.add_argument("--e2e-frames", type=int, default=1 << 20)
+    p.add_argument("--e2e-frames", type=int, default=1 << 21)
     p.add_argument("--ebn0", type=float, default=2.5)
     p.add_argument("--order", type=int, default=2)
     p.add_argument("--cpu-sample", type=int, default=40000, help="frames of the CPU baseline sample")
@@ -247,27 +247,41 @@ def run_ours(args):
     cwb = torch.empty((max(nfail, 1), 4), dtype=torch.int32, device=devs)
     osd_ms = timed(lambda: h.call("ldpcb_osd_decode", fl, fl, nfail, order, 0, 0, cwb, None, None, None, None, None, sp)) if nfail else 0.0
     peaks, peak_src = measured_peaks()
-    traffic = None
-    try:  # DRAM bytes per frame measured once under ncu (profiles/), scaled to the frames of this launch
+    traffic, prof = None, {}
+    try:  # per-frame DRAM bytes and warp instructions measured once under ncu (profiles/), scaled to this launch
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            tj = json.load(f)
-        per_frame = tj["osd_kernel" if osd_ms >= nms_ms else "nms_kernel"]["dram_bytes_per_frame"]
-        traffic = per_frame * (nfail if osd_ms >= nms_ms else B)
+            prof = json.load(f)
     except Exception:
-        traffic = None
+        prof = {}
     step_ms = total_ms / K
     dom_is_osd = osd_ms >= nms_ms
+    dom_key = "osd_kernel" if dom_is_osd else "nms_kernel"
     dom_ms = osd_ms if dom_is_osd else nms_ms
-    dom_bytes = (OSD_BYTES * nfail) if dom_is_osd else (NMS_BYTES * B)
+    dom_frames = nfail if dom_is_osd else B
+    dom_bytes = (OSD_BYTES if dom_is_osd else NMS_BYTES) * dom_frames
+    if dom_key in prof:
+        traffic = prof[dom_key]["dram_bytes_per_frame"] * dom_frames
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    sm_clock_hz = 1e6 * float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
+    issue_peak = h.sm_count * 4 * sm_clock_hz  # one warp instruction per scheduler (4 per SM) per cycle
+
+    def issue(key, frames, ms):
+        if key not in prof or "warp_instr_per_frame" not in prof[key] or not ms:
+            return None
+        rate = prof[key]["warp_instr_per_frame"] * frames / (ms * 1e-3)
+        return {"warp_instr_per_frame": prof[key]["warp_instr_per_frame"], "achieved_warp_instr_per_s": rate,
+                "peak_warp_instr_per_s": issue_peak, "frac": rate / issue_peak}
+
     roofline = {
-        "bound": "hbm", "kernel": "osd_kernel<2,false>" if dom_is_osd else "nms_kernel<5,3,false,false>",
+        "bound": "hbm", "kernel": "osd_kernel<2,false,true> (tensor-core pair sweep)" if dom_is_osd else "nms_kernel<5,3,true,false,false>",
         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
         "traffic": traffic, "traffic_source": "profiles/r01_traffic.json (ncu dram__bytes per frame x frames of this launch)" if traffic else None,
         "peak_source": peak_src, "kernel_ms": dom_ms, "share_of_step": dom_ms / step_ms,
         "algorithmic_bytes_per_launch": dom_bytes,
         "note": "both kernels are integer/FP32 issue-bound, not HBM-bound (SURVEY.md 8d): the HBM fraction is reported as BASELINE asks; "
-                "the binding resource is SM issue slots -- see profiles/ for sm__inst_executed / issue-active from ncu",
+                "the binding resource is SM issue slots -- `issue` gives warp instructions per frame (ncu sm__inst_executed, profiles/) x "
+                "frames/s of this run against SMs x 4 schedulers x the SM clock sampled in this run",
+        "issue": {"nms": issue("nms_kernel", B, nms_ms), "osd": issue("osd_kernel", nfail, osd_ms)},
         "kernels": {"nms_ms": nms_ms, "nms_frames_per_s": B / (nms_ms * 1e-3), "nms_GBps": NMS_BYTES * B / (nms_ms * 1e-3) / 1e9,
                     "osd_ms": osd_ms, "osd_frames": nfail, "osd_frames_per_s": (nfail / (osd_ms * 1e-3)) if osd_ms else None,
                     "osd_GBps": (OSD_BYTES * nfail / (osd_ms * 1e-3) / 1e9) if osd_ms else None},

@@ -153,6 +153,40 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned (&key)[4], unsigned (
     }
 }
 
+// The same network on single words (|y| bits with the low 7 bits replaced by the index): one shuffle and one min/max per
+// compare-exchange.  The order is exact unless two keys agree in their upper 24 bits, which the caller detects on
+// the sorted sequence (such keys end up adjacent) and repairs with the (key, index) sort above.
+__device__ __forceinline__ void bitonic_sort_desc_packed(unsigned (&v)[4], int lane) {
+#pragma unroll
+    for (int kk = 2; kk <= N; kk <<= 1) {
+#pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            if (j >= 4) {
+                const int lm = j >> 2;
+                const bool lower = (lane & lm) == 0;
+                const bool asc = (kk < N) && ((lane & (kk >> 2)) != 0);
+                const bool keep_min = (lower == asc);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned o = __shfl_xor_sync(0xffffffffu, v[k], lm);
+                    v[k] = keep_min ? min(v[k], o) : max(v[k], o);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if ((k & j) == 0) {
+                        const int i_bit = (kk == 2) ? (k & 2) : (kk == 4 ? (lane & 1) : (lane & (kk >> 2)));
+                        const bool asc = (kk < N) && (i_bit != 0);
+                        const unsigned a = v[k], b = v[k | j];
+                        v[k] = asc ? min(a, b) : max(a, b);
+                        v[k | j] = asc ? max(a, b) : min(a, b);
+                    }
+                }
+            }
+        }
+    }
+}
+
 // Registers a warp keeps about its frame between prepare and output.
 struct Prep {
     unsigned char pm[4];            // original index of permuted positions lane, lane+32 (MRB), lane+64, lane+96 (LRB)
@@ -187,13 +221,29 @@ __device__ __forceinline__ Prep prepare_frame(const OsdArgs& a, FrameSm& F, cons
         __syncwarp();
     } else {
         // ---- 1. sort --------------------------------------------------------------------
-        unsigned key[4] = {__float_as_uint(v.x) & 0x7fffffffu, __float_as_uint(v.y) & 0x7fffffffu,
-                           __float_as_uint(v.z) & 0x7fffffffu, __float_as_uint(v.w) & 0x7fffffffu};
-        unsigned idx[4] = {4u * lane, 4u * lane + 1, 4u * lane + 2, 4u * lane + 3};
-        bitonic_sort_desc(key, idx, lane);
-        const unsigned nxt = __shfl_down_sync(0xffffffffu, key[0], 1);
-        const bool tie = (key[0] == key[1]) || (key[1] == key[2]) || (key[2] == key[3]) || (lane < 31 && key[3] == nxt);
-        if (__any_sync(0xffffffffu, tie)) {
+        unsigned idx[4];
+        bool ties = false;  // warp-uniform
+        {
+            unsigned pk[4] = {(__float_as_uint(v.x) & 0x7fffff80u) | (4u * lane), (__float_as_uint(v.y) & 0x7fffff80u) | (4u * lane + 1),
+                              (__float_as_uint(v.z) & 0x7fffff80u) | (4u * lane + 2), (__float_as_uint(v.w) & 0x7fffff80u) | (4u * lane + 3)};
+            bitonic_sort_desc_packed(pk, lane);
+            const unsigned nx = __shfl_down_sync(0xffffffffu, pk[0], 1);
+            const bool close = ((pk[0] ^ pk[1]) < 128u) || ((pk[1] ^ pk[2]) < 128u) || ((pk[2] ^ pk[3]) < 128u) || (lane < 31 && (pk[3] ^ nx) < 128u);
+            if (__any_sync(0xffffffffu, close)) {  // two keys share their upper 24 bits (~4 % of AWGN frames): exact (key, index) sort
+                unsigned key[4] = {__float_as_uint(v.x) & 0x7fffffffu, __float_as_uint(v.y) & 0x7fffffffu,
+                                   __float_as_uint(v.z) & 0x7fffffffu, __float_as_uint(v.w) & 0x7fffffffu};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) idx[k] = 4u * lane + k;
+                bitonic_sort_desc(key, idx, lane);
+                const unsigned nxt = __shfl_down_sync(0xffffffffu, key[0], 1);
+                const bool tie = (key[0] == key[1]) || (key[1] == key[2]) || (key[2] == key[3]) || (lane < 31 && key[3] == nxt);
+                ties = __any_sync(0xffffffffu, tie);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) idx[k] = pk[k] & 0x7fu;
+            }
+        }
+        if (ties) {
             // exact rank sort with the tf.argsort tie rule (stable: lower index first; reversed-ascending: higher first)
             __syncwarp();
             unsigned mykey[4];

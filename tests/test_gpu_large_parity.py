@@ -48,14 +48,16 @@ def test_osd_many_frames_bit_exact(handle, code, order, n, tep_order, flags):
         assert np.array_equal(got[k], ref[k]), k
 
 
-def test_osd_quantised_inputs_many_ties(handle, code):
-    """Every frame has many equal |y|: the exact tie path of the sort, at scale."""
+@pytest.mark.parametrize("order,n", [(1, 8000), (2, 3000)])
+def test_osd_quantised_inputs_many_ties(handle, code, order, n):
+    """Every frame has many equal |y|: the exact tie path of the sort and, at order 2, the exact 64-bit fallback
+    of the tensor-core pair sweep (many candidates share the truncated minimum), at scale."""
     y, cw, _ = PO.gen_frames(99, 0, 30000, 2.0, code.G)
     yq = (np.round(y * 8) / 8).astype(np.float32)
-    teps = OO.pack_teps(OO.generate_teps_conv(1))
+    teps = OO.pack_teps(OO.generate_teps_conv(order))
     for flags in (0, 1):
-        ref = CO.osd(yq[:8000], None, code.G, teps, flags=flags)
-        got = osd_gpu(handle, yq[:8000], order=1, flags=flags)
+        ref = CO.osd(yq[:n], None, code.G, teps, flags=flags)
+        got = osd_gpu(handle, yq[:n], order=order, flags=flags)
         for k in ("perm", "best_tep", "best_score_q", "codeword", "redG"):
             assert np.array_equal(got[k], ref[k]), (flags, k)
 

@@ -138,3 +138,36 @@ def test_counter_allreduce_two_ranks_gloo(tmp_path):
                           "--master-port", "29517", str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_exported_weights_round_trip(tmp_path):
+    """weights.npz / decoding_path.json as scripts/export_tf_weights.py writes them."""
+    import json
+
+    from short_ldpc_decoding_osd_b200 import nn_net, weights
+
+    rng = np.random.default_rng(0)
+    w = {"nms_check": np.array([-0.048], np.float32), "k1": rng.normal(size=(3, 1, 8)), "k2": rng.normal(size=(3, 8, 4)),
+         "k3": rng.normal(size=(3, 4, 2)), "dense_w": rng.normal(size=(14, 1)), "dense_b": np.array([0.1]),
+         "fcn1": rng.normal(size=(6, 6)), "fcn2": rng.normal(size=(6, 2))}
+    p = tmp_path / "weights.npz"
+    np.savez(p, **w)
+    got = weights.load_npz(str(p))
+    assert abs(weights.alpha_of(got) - 0.66943514) < 1e-6
+    taps, bias = nn_net.fold_conv_bitwise(got["k1"], got["k2"], got["k3"], got["dense_w"], got["dense_b"])
+    # the folded FIR equals the three linear convolutions + dense layer on a random trajectory
+    x = rng.normal(size=13)
+    h = x.reshape(-1, 1)
+    for k in (w["k1"], w["k2"], w["k3"]):
+        h = np.stack([np.einsum("dc,dco->o", h[t:t + 3], k) for t in range(h.shape[0] - 2)])
+    want = float(h.reshape(-1) @ w["dense_w"].reshape(-1) + 0.1)
+    assert abs(float(taps.astype(np.float64) @ x + bias) - want) < 1e-4
+    fcn = weights.make_fcn(got)
+    pr = fcn(rng.normal(size=(3, 6)).astype(np.float32))
+    assert pr.shape == (3, 2) and np.allclose(pr.sum(1), 1.0, atol=1e-6)
+    np.savez(p, k1=np.zeros((3, 2, 8)))
+    with pytest.raises(ValueError):
+        weights.load_npz(str(p))
+    q = tmp_path / "path.json"
+    q.write_text(json.dumps({"decoding_path": [[0, 0, 0, 0, 0, 0], [1, 0, 0, 0, 0, 0], [0, 1, 0, 0, 0, 0]], "counts": [9, 5, 2]}))
+    assert weights.load_decoding_path(str(q))[1] == [1, 0, 0, 0, 0, 0]
