@@ -278,47 +278,65 @@ __device__ __forceinline__ Prep prepare_frame(const OsdArgs& a, FrameSm& F, cons
         }
         {
             unsigned used_lo = 0u, used_hi = 0u;
-            int npiv = 0, nlrb = 0, l = 0;
-            // once the basis is complete no row is free, so the remaining columns of a group of four fall through the
-            // "dependent" branch, which is what they are: the count is only tested once per group
+            int npiv = 0, l = 0;
+            unsigned pvb[4] = {0u, 0u, 0u, 0u};  // pivot-row bit (within its 32-bit half) of my column k, 0 = not a pivot
+            unsigned pvh = 0u;                   // bit k: that row lies in the high half
+            // Once the basis is complete no row is free, so the remaining columns of a group of four fall through as
+            // dependent, which is what they are: the count is only tested once per group.  The loop keeps no lists:
+            // the owner lane notes its pivots and the MRB / LRB position lists are built afterwards by a prefix sum.
             for (; l < 32 && npiv < K; ++l) {
+                const bool mine = (lane == l);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const int c = 4 * l + k;
                     const unsigned cl = __shfl_sync(0xffffffffu, clo[k], l);
                     const unsigned ch = __shfl_sync(0xffffffffu, chi[k], l);
                     const unsigned al = cl & ~used_lo, ah = ch & ~used_hi;
-                    if ((al | ah) == 0u) {  // dependent on more reliable columns
-                        if (lane == 0) F.pos[K + nlrb] = (unsigned char)c;
-                        ++nlrb;
-                    } else {
-                        int p;
+                    if ((al | ah) != 0u) {  // else: dependent on more reliable columns
                         if (al != 0u) {  // pivot row in the low word (any unused row with a 1 gives the same basis)
                             const unsigned bit = al & (0u - al);
-                            p = 31 - __clz(bit);
                             used_lo |= bit;
                             const unsigned ml = cl ^ bit;
                             if ((ml | ch) != 0u) {  // an untouched unit column (information position of G) needs no row operation
 #pragma unroll
                                 for (int kk = 0; kk < 4; ++kk) xor_if_bit(clo[kk], chi[kk], clo[kk], bit, ml, ch);
                             }
+                            if (mine) pvb[k] = bit;
                         } else {
                             const unsigned bit = ah & (0u - ah);
-                            p = 63 - __clz(bit);
                             used_hi |= bit;
                             const unsigned mh = ch ^ bit;
                             if ((cl | mh) != 0u) {
 #pragma unroll
                                 for (int kk = 0; kk < 4; ++kk) xor_if_bit(clo[kk], chi[kk], chi[kk], bit, cl, mh);
                             }
+                            if (mine) { pvb[k] = bit; pvh |= 1u << k; }
                         }
-                        if (lane == 0) { F.pos[npiv] = (unsigned char)c; F.prow_of[npiv] = (unsigned char)p; }
                         ++npiv;
                     }
                 }
             }
-            // basis complete: every remaining position is LRB
-            for (int t = 4 * l + lane; t < N; t += 32) F.pos[K + nlrb + t - 4 * l] = (unsigned char)t;
+            // position lists: MRB = pivot columns, LRB = the others, both in scan (reliability) order
+            const int cnt = (pvb[0] != 0u) + (pvb[1] != 0u) + (pvb[2] != 0u) + (pvb[3] != 0u);
+            int pre = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, pre, d);
+                if (lane >= d) pre += t;
+            }
+            int r = pre - cnt;      // pivots before my first column
+            int q = 4 * lane - r;   // non-pivots before my first column
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned char c = (unsigned char)(4 * lane + k);
+                if (pvb[k] != 0u) {
+                    F.pos[r] = c;
+                    F.prow_of[r] = (unsigned char)(((pvh >> k) & 1u) * 32u + 31u - __clz(pvb[k]));
+                    ++r;
+                } else {
+                    F.pos[K + q] = c;
+                    ++q;
+                }
+            }
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) cols[4 * lane + k] = ((unsigned long long)chi[k] << 32) | clo[k];
