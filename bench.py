@@ -288,7 +288,7 @@ def run_ours(args):
     }
 
     # ---- end to end through the host-buffer C-ABI call -------------------------------------------
-    Be = args.e2e_frames
+    Be = min(args.e2e_frames, B)
     yh = _lib.pinned_empty((Be, 128), np.float32)
     th = _lib.pinned_empty((Be, 4), np.uint32)
     bh = _lib.pinned_empty((Be, 4), np.uint32)
