@@ -174,9 +174,20 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     devs = f"cuda:{local_rank}"
     if world > 1:
-        # keep stdout to the one JSON line: NCCL's version banner and debug output go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device(devs))
+        # keep stdout to the one JSON line: NCCL prints its version banner with printf when the communicator is
+        # created, so fd 1 points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(devs))
+            warm = torch.zeros(1, device=devs)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     code = Code()
     h = _lib.Handle(code.H, code.G, device=local_rank)
     B, K, W, order = args.frames, args.steps, max(args.warmup, 3), args.order

@@ -18,9 +18,11 @@ ALPHA = 0.66943514
 rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
 torch.cuda.set_device(local)
 dev = f"cuda:{local}"
-if world > 1:
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+if world > 1:  # NCCL's version banner (printf at communicator creation) goes to stderr
+    sys.stdout.flush(); _fd = os.dup(1); os.dup2(2, 1)
     dist.init_process_group("nccl", device_id=torch.device(dev))
+    dist.all_reduce(torch.zeros(1, device=dev)); torch.cuda.synchronize()
+    sys.stdout.flush(); os.dup2(_fd, 1); os.close(_fd)
 code = Code()
 h = _lib.Handle(code.H, code.G, device=local)
 lo, hi = 10, int(os.environ.get("SWEEP_MAX_LOG2", "24"))
