@@ -78,3 +78,29 @@ def test_fer_matches_reference_points(handle, golden_dir):
                 assert abs(ours - theirs) <= 3.5 * se + 1e-12, (pt["ebn0_db"], order, ours, theirs, se)
                 inside.append(ci[0] <= ours <= ci[1])
     assert np.mean(inside) >= 0.8  # a 95% interval of an independent estimate is missed ~5% of the time by chance
+
+
+@pytest.mark.parametrize("tep_order,ebn0", [(0, 2.0), (1, 3.0)])
+def test_pair_sweep_equals_lut_sweep_on_a_million_frames(handle, tep_order, ebn0):
+    """The tensor-core pair sweep (order-2 lists, truncated scores + exact re-scoring of the window) against the
+    exact 64-bit byte-LUT sweep of the same kernel family (block-minima path, one block = the whole list) on 2^20
+    device-generated frames: first-minimum index and exact score must agree on every frame."""
+    B = 1 << 20
+    y = empty((B, 128), torch.float32)
+    tr = empty((B, 4), torch.int32)
+    handle.call("ldpcb_gen_frames", 9091 + tep_order, 0, B, float(ebn0), y, tr, None)
+    cw = empty((B, 4), torch.int32)
+    bt = empty((B,), torch.int32)
+    bq = empty((B,), torch.int64)
+    ex = empty((B,), torch.int32)
+    handle.call("ldpcb_osd_decode", y, y, B, 2, tep_order, 0, cw, bt, bq, ex, None, None, None)
+    teps = handle.tep_table(2, tep_order)
+    starts = np.array([0, len(teps)], np.int32)
+    bm = empty((B, 1), torch.int64)
+    ba = empty((B, 1), torch.int32)
+    ex2 = empty((B,), torch.int32)
+    handle.call("ldpcb_osd_block_minima", y, y, B, dev(teps.view(np.int32)), len(teps), dev(starts), 1, 0, bm, ba, ex2, None, None, None, None)
+    sync()
+    assert torch.equal(ex, ex2)
+    assert torch.equal(bq, bm[:, 0])
+    assert torch.equal(bt, ba[:, 0])
