@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import c_oracle as CO
 from oracle import nms_oracle as NO
 from oracle import osd_oracle as OO
 from oracle import philox_oracle as PO
@@ -244,3 +245,54 @@ def test_tep_tables_match_oracle(handle):
         assert handle.tep_count(order, 0) == n and handle.tep_count(order, 1) == n
         assert np.array_equal(handle.tep_table(order, 0), OO.pack_teps(OO.generate_teps_conv(order)))
         assert np.array_equal(handle.tep_table(order, 1), OO.pack_teps(OO.generate_teps_fs(order)))
+
+
+# ---- another (128,64) code: the generic instantiations ---------------------------------------------------------
+def _other_code():
+    """H = [A | I], G = [I | A^T] with A a sum of six or seven 64x64 circulant permutations: check degrees 7 and 8
+    (padded edge slots), variable degrees 6..7 and 1 -- none of the CCSDS fast-path assumptions hold."""
+    A = np.zeros((64, 64), dtype=np.uint8)
+    for s in (1, 5, 11, 24, 37, 50):
+        A[np.arange(64), (np.arange(64) + s) % 64] = 1
+    rows = np.arange(0, 64, 3)
+    A[rows, (rows + 58) % 64] = 1
+    H = np.concatenate([A, np.eye(64, dtype=np.uint8)], axis=1)
+    G = np.concatenate([np.eye(64, dtype=np.uint8), A.T], axis=1)
+    assert not ((H.astype(np.int64) @ G.T.astype(np.int64)) % 2).any()
+    assert H.sum(1).max() <= 8 and H.sum(0).max() <= 8
+    return H, G
+
+
+def test_other_code_nms_and_osd(code):
+    H, G = _other_code()
+    h = _lib.Handle(H, G, device=0)
+    try:
+        y, cw, _ = PO.gen_frames(21, 0, 600, 3.0, G)
+        assert not ((cw.astype(np.int64) @ H.T.astype(np.int64)) % 2).any()
+        ref = NO.decode(y, H, 12, ALPHA)
+        got = nms_gpu(h, y, 12, ALPHA)
+        check_nms(got, ref, 12)
+        for w_vc, w_marg in ((0.8, 1.1),):
+            ref2 = NO.decode(y[:100], H, 7, 0.75, w_vc, w_marg)
+            got2 = nms_gpu(h, y[:100], 7, 0.75, w_vc, w_marg)
+            check_nms(got2, ref2, 7)
+        fails = np.flatnonzero(ref["syndrome_nz"])[:12]
+        assert len(fails) >= 4
+        for order in (1, 2):
+            teps = OO.generate_teps_conv(order)
+            o = osd_gpu(h, y[fails], order=order)
+            for i, f in enumerate(fails):
+                check_osd_frame(o, i, OO.osd_frame(y[f], y[f], G, teps), code)
+        # the whole pipeline on this code: decisions of detected failures replaced by order-2 OSD
+        B = len(y)
+        bits = np.empty((B, 4), np.uint32)
+        syn = np.empty(B, np.uint8)
+        cnt = np.zeros(16, np.uint64)
+        h.call("ldpcb_decode_host", y, B, 12, ALPHA, 1.0, 1.0, 0, 2, 0, bits, syn, None, _lib.pack_bits(cw), cnt)
+        want = ref["hard"].copy()
+        allf = np.flatnonzero(ref["syndrome_nz"])
+        want[allf] = CO.osd(np.ascontiguousarray(y[allf]), None, G, OO.pack_teps(OO.generate_teps_conv(2)))["codeword"]
+        assert np.array_equal(_lib.unpack_bits(bits), want)
+        assert int(cnt[0]) == B and int(cnt[9]) == int((want != cw).any(1).sum())
+    finally:
+        h.close()
