@@ -241,7 +241,8 @@ int ldpcb_osd_fs_decode_host(ldpcb_t* h, const float* llr_host, int64_t B, int o
  * PB-OSD (probability-based OSD) policy.  Replaces the per-frame body of pb_osd(snr, selected_ds)
  * (PB_OSD/pb_testing.py:100-149): best-first TEP order (optimal_tep_sequence, :366-397), promising-probability
  * stop (:128-132, :399-447) and success-probability stop (:137-149, :410-423) with the thresholds of
- * calculate_two_thresholds (:485-500).  order_limit 0..2.
+ * calculate_two_thresholds (:485-500).  order_limit 0..3 (3 is the reference's default, PB_OSD/globalmap.py:42; its
+ * 43,745-entry TEP lists live in a global-memory workspace owned by the handle, orders 0..2 keep them in shared memory).
  *   llr_dev [B,128] channel LLR of the frames; snr_db the Eb/N0 the reference passes as `snr` (:50-52)
  *   cw_bits_dev [B,4] out: optimal_codeword, original bit positions
  *   stats_dev [B,4] int32 out (may be NULL): TEPs visited (cost_tep_num or N_max), p_e^pro passes

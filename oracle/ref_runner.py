@@ -235,7 +235,7 @@ def run_pb():
 
     y, lab = _failed(code, 36, 5)
     res = {}
-    for order, snr in ((1, 2.5), (2, 2.5), (2, 3.5)):
+    for order, snr in ((1, 2.5), (2, 2.5), (2, 3.5), (3, 2.5)):  # order_limit 3 is the reference's default (PB_OSD/globalmap.py:42)
         GL.set_map("order_limit", order)
         S, NT, ML, A1, A2 = [], [], [], [], []
         for i in range(len(y)):

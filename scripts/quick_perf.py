@@ -44,7 +44,7 @@ for order in (1, 2):
     t = timeit(lambda: h.call('ldpcb_osd_fs_decode', yf, Bf, order, 6.5, 30, 6.4, bits, None, nt, sk, None, None, None, None), n=3, warm=1)
     print('fs-osd order', order, t, 'frames/s %.3e' % (Bf / t[0] * 1e3), 'avg teps %.1f' % nt[:Bf].float().mean().item())
 st4 = torch.empty((Bf, 4), dtype=torch.int32, device='cuda')
-for order in (1, 2):
+for order in (1, 2, 3):
     Bp = Bf if order == 1 else Bf // 4
     t = timeit(lambda: h.call('ldpcb_osd_pb_decode', yf, Bp, order, 2.5, bits, st4, None, None, None), n=3, warm=1)
     print('pb-osd order', order, t, 'frames/s %.3e' % (Bp / t[0] * 1e3), 'avg teps %.1f' % st4[:Bp, 0].float().mean().item())

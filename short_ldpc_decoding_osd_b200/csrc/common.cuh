@@ -81,6 +81,8 @@ struct ldpcb_handle {
     ldpcb::TepTable tep[4][2];      // [order][tep_order]
     int32_t* one_block_dev = nullptr;  // {0, n} scratch for single-block calls
     ldpcb::Workspace ws[ldpcb::NUM_WS];
+    char* pb_list = nullptr;       // PB-OSD order 3: TEP lists of the resident warps
+    size_t pb_list_cap = 0;        // in list entries
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t events[3] = {nullptr, nullptr, nullptr};
     uint64_t launches = 0;
@@ -165,6 +167,9 @@ struct PbParams {
     int order;            // order_limit (0..2)
     int32_t* stats;       // [B,4] out: TEPs visited, p_e^pro passes, improvements, list comparisons
     double cdf_half[65];  // BinCDF(b; 64, 1/2)
+    long long* glist_sum; // order 3: per-warp TEP lists in global memory (set by the launcher)
+    long long* glist_bmin; // order 3: minima of every 32 list entries
+    unsigned* glist_tep;
 };
 int launch_osd_pb(ldpcb_handle* h, const OsdArgs& a, const PbParams& pp, cudaStream_t st);
 

@@ -381,6 +381,7 @@ void ldpcb_destroy(ldpcb_t* h) {
         }
     for (int i = 0; i < NUM_WS; ++i)
         if (h->ws[i].buf) cudaFree(h->ws[i].buf);
+    if (h->pb_list) cudaFree(h->pb_list);
     for (int i = 0; i < 3; ++i) {
         if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
         if (h->events[i]) cudaEventDestroy(h->events[i]);

@@ -15,13 +15,17 @@
 
 namespace ldpcb {
 
-constexpr int PB_MAX_LIST = 2081;  // every non-zero TEP of weight <= 2 is pushed exactly once
+constexpr int PB_MAX_LIST = 2081;   // every non-zero TEP of weight <= 2 is pushed exactly once
+constexpr int PB_GLIST_CAP = 43776;  // order 3: 43,745 TEPs, the list of a warp lives in global memory (L2 in practice)
 
-struct __align__(16) PbFrameSm {
+struct __align__(16) PbHead {
     FrameSm fr;
+    double cdf_p1[66];                 // BinCDF(b; 64, p1)
+};
+struct __align__(16) PbFrameSm {
+    PbHead h;
     long long lsum[PB_MAX_LIST + 3];   // MRB weight of the live TEPs in insertion order (tombstone = INT64_MAX)
     unsigned ltep[PB_MAX_LIST + 3];    // packed positions
-    double cdf_p1[66];                 // BinCDF(b; 64, p1)
 };
 
 __constant__ double c_binom64[65];  // C(64, i)
@@ -43,16 +47,32 @@ __device__ __forceinline__ float mean64_pairwise(const float* v, int lane) {
     return __shfl_sync(0xffffffffu, r, 0) * 0.015625f;
 }
 
+// GLIST: the TEP list of each warp is a slice of pp.glist_sum / pp.glist_tep instead of shared memory
+template <bool GLIST>
 __global__ void __launch_bounds__(OSD_THREADS) osd_pb_kernel(OsdArgs a, PbParams pp, const uint64_t* __restrict__ gcol) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    PbFrameSm* all = reinterpret_cast<PbFrameSm*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    PbFrameSm& W = all[warp];
+    PbHead& W = GLIST ? reinterpret_cast<PbHead*>(smem_raw)[warp] : reinterpret_cast<PbFrameSm*>(smem_raw)[warp].h;
+    const int64_t slice = ((int64_t)blockIdx.x * OSD_FPB + warp) * PB_GLIST_CAP;
+    long long* const lsum = GLIST ? pp.glist_sum + slice : reinterpret_cast<PbFrameSm*>(smem_raw)[warp].lsum;
+    unsigned* const ltep = GLIST ? pp.glist_tep + slice : reinterpret_cast<PbFrameSm*>(smem_raw)[warp].ltep;
+    // GLIST: minimum of every 32 consecutive list entries, so that a pop scans nslots/32 values instead of nslots
+    long long* const bmin = GLIST ? pp.glist_bmin + ((int64_t)blockIdx.x * OSD_FPB + warp) * (PB_GLIST_CAP / 32) : nullptr;
+    auto refresh_block = [&](int b, int n) {  // n = current list length; all lanes
+        const int i = b * 32 + lane;
+        long long s = i < n ? lsum[i] : 0x7fffffffffffffffll;
+#pragma unroll
+        for (int m = 16; m; m >>= 1) {
+            const long long o = (long long)shfl_xor64((unsigned long long)s, m);
+            s = o < s ? o : s;
+        }
+        if (lane == 0) bmin[b] = s;
+    };
     FrameSm& F = W.fr;
     const int64_t nframes = a.count ? (int64_t)*a.count : a.B;
     const int64_t gw = (int64_t)blockIdx.x * OSD_FPB + warp;
     const int64_t nw = (int64_t)gridDim.x * OSD_FPB;
-    const int n_max = pp.order <= 0 ? 1 : (pp.order == 1 ? 65 : 2081);
+    const int n_max = pp.order <= 0 ? 1 : (pp.order == 1 ? 65 : (pp.order == 2 ? 2081 : 43745));
 
     for (int64_t f = gw; f < nframes; f += nw) {
         const int64_t row = a.idx ? (int64_t)a.idx[f] : f;
@@ -111,7 +131,11 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_pb_kernel(OsdArgs a, PbParams
         unsigned long long opt_D = d0, opt_flip = 0ull;
         // list initialised with the TEP {k-1}
         int nslots = 1, live = 1;
-        if (lane == 0) { W.lsum[0] = F.qd[K - 1]; W.ltep[0] = 0xffffff00u | (unsigned)(K - 1); }
+        if (lane == 0) {
+            lsum[0] = F.qd[K - 1];
+            ltep[0] = 0xffffff00u | (unsigned)(K - 1);
+            if (GLIST) bmin[0] = F.qd[K - 1];
+        }
         __syncwarp();
         int cost = 0, early = 0, suc1 = 0, suc2 = 0, list_cmp = 0;
         for (int j = 0; j < n_max - 1; ++j) {
@@ -119,12 +143,26 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_pb_kernel(OsdArgs a, PbParams
             // pop the first minimum
             long long bs = 0x7fffffffffffffffll;
             int bi = 0x7fffffff;
-            for (int i = lane; i < nslots; i += 32) {
-                const long long s = W.lsum[i];
-                if (s < bs) { bs = s; bi = i; }
+            if (GLIST) {
+                // the first block holding the minimum holds the first minimum
+                const int nb = (nslots + 31) >> 5;
+                for (int b = lane; b < nb; b += 32) {
+                    const long long s = bmin[b];
+                    if (s < bs) { bs = s; bi = b; }
+                }
+                warp_argmin(bs, bi);
+                const int i = bi * 32 + lane;
+                bs = i < nslots ? lsum[i] : 0x7fffffffffffffffll;
+                bi = i;
+                warp_argmin(bs, bi);
+            } else {
+                for (int i = lane; i < nslots; i += 32) {
+                    const long long s = lsum[i];
+                    if (s < bs) { bs = s; bi = i; }
+                }
+                warp_argmin(bs, bi);
             }
-            warp_argmin(bs, bi);
-            const unsigned tw = W.ltep[bi];
+            const unsigned tw = ltep[bi];
             const long long wsum = bs;
             // successors (uniform), written by lane 0
             unsigned pos[3];
@@ -151,14 +189,22 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_pb_kernel(OsdArgs a, PbParams
             }
             __syncwarp();
             if (lane == 0) {
-                W.lsum[bi] = 0x7fffffffffffffffll;
-                if (do_ext) { W.lsum[nslots] = s_ext; W.ltep[nslots] = t_ext; }
-                if (do_adj) { W.lsum[nslots + (do_ext ? 1 : 0)] = s_adj; W.ltep[nslots + (do_ext ? 1 : 0)] = t_adj; }
+                lsum[bi] = 0x7fffffffffffffffll;
+                if (do_ext) { lsum[nslots] = s_ext; ltep[nslots] = t_ext; }
+                if (do_adj) { lsum[nslots + (do_ext ? 1 : 0)] = s_adj; ltep[nslots + (do_ext ? 1 : 0)] = t_adj; }
             }
             add = (do_ext ? 1 : 0) + (do_adj ? 1 : 0);
+            const int nslots_old = nslots;
             nslots += add;
             live += add - 1;
             __syncwarp();
+            if (GLIST) {
+                const int b0 = bi >> 5, b1 = nslots_old >> 5, b2 = (nslots - 1) >> 5;
+                refresh_block(b0, nslots);
+                if (add > 0 && b1 != b0) refresh_block(b1, nslots);
+                if (add > 0 && b2 != b1 && b2 != b0) refresh_block(b2, nslots);
+                __syncwarp();
+            }
             // candidate
             unsigned long long D = d0, flip = 0ull;
             float rel = 0.0f;
@@ -242,19 +288,47 @@ int launch_osd_pb(ldpcb_handle* h, const OsdArgs& a, const PbParams& pp, cudaStr
         LDPCB_CUDA(h, cudaMemcpyToSymbol(c_binom64, c, sizeof c));
         consts_ready[h->device & 7] = true;
     }
+    if (pp.order >= 3) {
+        // lists in global memory: one slice per resident warp
+        const int smem = OSD_FPB * (int)sizeof(PbHead);
+        static thread_local int occ_g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int& occ = occ_g[h->device & 7];
+        if (occ == 0) {
+            LDPCB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, osd_pb_kernel<true>, OSD_THREADS, smem));
+            if (occ < 1) occ = 1;
+            if (occ > 4) occ = 4;  // 16 warps per SM: 148 x 16 x 43,776 x 12 B = 1.2 GB of lists
+        }
+        int64_t want = (a.B + OSD_FPB - 1) / OSD_FPB;
+        int64_t cap = (int64_t)h->sm_count * occ;
+        int grid = (int)(want < cap ? want : cap);
+        if (grid < 1) grid = 1;
+        const size_t per = (size_t)grid * OSD_FPB * PB_GLIST_CAP;
+        if (h->pb_list_cap < per) {
+            if (h->pb_list) { LDPCB_CUDA(h, cudaDeviceSynchronize()); LDPCB_CUDA(h, cudaFree(h->pb_list)); h->pb_list = nullptr; h->pb_list_cap = 0; }
+            LDPCB_CUDA(h, cudaMalloc(&h->pb_list, per * (sizeof(long long) + sizeof(unsigned)) + per / 32 * sizeof(long long)));
+            h->pb_list_cap = per;
+        }
+        PbParams q = pp;
+        q.glist_sum = reinterpret_cast<long long*>(h->pb_list);
+        q.glist_bmin = reinterpret_cast<long long*>(h->pb_list + per * sizeof(long long));
+        q.glist_tep = reinterpret_cast<unsigned*>(h->pb_list + per * sizeof(long long) + per / 32 * sizeof(long long));
+        osd_pb_kernel<true><<<grid, OSD_THREADS, smem, st>>>(a, q, h->gcol_dev);
+        LDPCB_LAUNCH_CHECK(h, "osd_pb_kernel<global list>");
+        return LDPCB_OK;
+    }
     const int smem = OSD_FPB * (int)sizeof(PbFrameSm);
     static thread_local int occ_cache[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int& occ = occ_cache[h->device & 7];
     if (occ == 0) {
-        LDPCB_CUDA(h, cudaFuncSetAttribute(osd_pb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        LDPCB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, osd_pb_kernel, OSD_THREADS, smem));
+        LDPCB_CUDA(h, cudaFuncSetAttribute(osd_pb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        LDPCB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, osd_pb_kernel<false>, OSD_THREADS, smem));
         if (occ < 1) occ = 1;
     }
     int64_t want = (a.B + OSD_FPB - 1) / OSD_FPB;
     int64_t cap = (int64_t)h->sm_count * occ;
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
-    osd_pb_kernel<<<grid, OSD_THREADS, smem, st>>>(a, pp, h->gcol_dev);
+    osd_pb_kernel<false><<<grid, OSD_THREADS, smem, st>>>(a, pp, h->gcol_dev);
     LDPCB_LAUNCH_CHECK(h, "osd_pb_kernel");
     return LDPCB_OK;
 }
@@ -267,8 +341,8 @@ extern "C" int ldpcb_osd_pb_decode(ldpcb_t* h, const float* llr_dev, int64_t B, 
                                    uint32_t* cw_bits_dev, int32_t* stats_dev, int64_t* best_score_q_dev,
                                    int32_t* score_exp_dev, void* stream) {
     if (!h) return LDPCB_ERR_ARG;
-    if (B < 0 || order_limit < 0 || order_limit > 2)
-        return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_pb_decode: B=%lld order_limit=%d out of range (0..2)", (long long)B, order_limit);
+    if (B < 0 || order_limit < 0 || order_limit > 3)
+        return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_pb_decode: B=%lld order_limit=%d out of range (0..3)", (long long)B, order_limit);
     if (B == 0) return LDPCB_OK;
     if (!llr_dev || !cw_bits_dev) return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_pb_decode: NULL llr or cw_bits");
     if ((uintptr_t)llr_dev & 15) return set_error(h, LDPCB_ERR_ALIGN, "ldpcb_osd_pb_decode: llr must be 16-byte aligned");
@@ -280,6 +354,9 @@ extern "C" int ldpcb_osd_pb_decode(ldpcb_t* h, const float* llr_dev, int64_t B, 
     pp.c4 = (float)(-4.0 * nv);
     pp.order = order_limit;
     pp.stats = stats_dev;
+    pp.glist_sum = nullptr;
+    pp.glist_bmin = nullptr;
+    pp.glist_tep = nullptr;
     {   // BinCDF(b; 64, 1/2) in fp64, cumulative in index order
         unsigned __int128 e = 1;
         double acc = 0.0;

@@ -10,9 +10,9 @@
 * ``miracle_view`` -- pb_testing.py:502-511, the genie statistic (MRB hard-decision errors per frame).
 * ``pb_osd(snr, selected_ds)`` -- pb_testing.py:44-229 driver.  With ``GL.pb_osd`` set the PB policy (best-first
   TEP order, p_e^pro / p_e^suc stopping, :100-149,366-500) runs for all frames in one call of
-  ldpcb_osd_pb_decode_host (order_limit <= 2; order 3 would need a 43,745-entry list per frame and falls back
-  to the exhaustive sweep, logged as such); the ``convention_osd`` and ``miracle_view`` switches are served by
-  the exhaustive GPU sweep.  Same log lines as the reference.
+  ldpcb_osd_pb_decode_host (order_limit 0..3; at order 3, the reference's default, the 43,745-entry TEP lists
+  live in global memory); the ``convention_osd`` and ``miracle_view`` switches are served by the exhaustive GPU
+  sweep.  Same log lines as the reference.
 * ``pb_osd_batch(inputs, labels, snr, order_limit)`` -- the policy on [B,128] arrays.
 """
 from __future__ import annotations
@@ -128,7 +128,7 @@ def pb_osd(snr, selected_ds):
         summary["miracle"] = dict(counter_stat)
         return summary
     limit = GL.get_map("termination_num_threshlod") or 100
-    if GL.get_map("pb_osd") and not GL.get_map("convention_osd") and order_limit <= 2:
+    if GL.get_map("pb_osd") and not GL.get_map("convention_osd"):
         res = pb_osd_batch(y, lab, snr, order_limit)
         fails_cum = np.cumsum(~res["correct"])
         n_used = int(np.searchsorted(fails_cum, limit) + 1) if fails_cum.size and fails_cum[-1] >= limit else len(y)
@@ -161,7 +161,7 @@ def pb_osd(snr, selected_ds):
     counter = Counter(int(p) for p in res["phase"][:n_used])
     FER = round(F / max(S + F, 1), 4)
     T2 = time.process_time()
-    tag = "CNV-OSD" if GL.get_map("convention_osd") else "PB-OSD(order 3: exhaustive sweep, stopping rule not applied)"
+    tag = "CNV-OSD" if GL.get_map("convention_osd") else "OSD(exhaustive sweep: neither pb_osd nor convention_osd is set)"
     log_filename = logdir + ("CNV-OSD-order-" if GL.get_map("convention_osd") else "PB-OSD-order-") + str(order_limit) + ".txt"
     print("\nFor %s %.1fdB (order_limit:%d) :\n" % (tag, snr, order_limit))
     print("----> S:" + str(S) + " F:" + str(F) + "\n")

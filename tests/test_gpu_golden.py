@@ -191,7 +191,7 @@ def test_pb_kernel_matches_reference_policy(handle, golden_dir):
 
     g = load(golden_dir, "pb_ref_shim.npz")
     G = load(golden_dir, "code_ref.npz")["G"].astype(np.int64)
-    for order, snr, tag in ((1, 2.5, "o1_snr25"), (2, 2.5, "o2_snr25"), (2, 3.5, "o2_snr35")):
+    for order, snr, tag in ((1, 2.5, "o1_snr25"), (2, 2.5, "o2_snr25"), (2, 3.5, "o2_snr35"), (3, 2.5, "o3_snr25")):
         res = P.pb_osd_batch(g["y"], g["labels"], snr, order)
         assert np.array_equal(res["correct"].astype(int), g[f"success_{tag}"])
         assert np.array_equal(res["num_teps"], g[f"num_teps_{tag}"])
@@ -210,7 +210,7 @@ def test_pb_policy_on_more_frames(handle, code):
     y, cw, _ = PO.gen_frames(123, 0, 1500, 2.5, code.G)
     syn = nms_gpu(handle, y, 12, traj=False)["syndrome_nz"]
     yf, cf = y[syn][:150], cw[syn][:150]
-    for order, snr in ((2, 2.5), (1, 3.0), (0, 2.5)):
+    for order, snr in ((2, 2.5), (1, 3.0), (0, 2.5), (3, 3.0)):
         res = P.pb_osd_batch(yf, cf, snr, order)
         mism = 0
         for i in range(len(yf)):
