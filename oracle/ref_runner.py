@@ -190,12 +190,13 @@ def run_fs():
 
     y, lab = _failed(code, 30, 3)
     res = {}
-    for order in (1, 2):
+    for order in (1, 2, 3):  # order_limit 3 is the reference's default (FS_OSD/globalmap.py:44): first 12 frames only (slow)
         GL.set_map("order_limit", order)
-        seq = R.generate_sequential_teps(64, order)
-        res[f"seq{order}"] = np.packbits(np.concatenate([np.asarray(s) for s in seq], 0).astype(np.uint8), axis=1)
+        if order < 3:
+            seq = R.generate_sequential_teps(64, order)
+            res[f"seq{order}"] = np.packbits(np.concatenate([np.asarray(s) for s in seq], 0).astype(np.uint8), axis=1)
         S, NT = [], []
-        for i in range(len(y)):
+        for i in range(len(y) if order < 3 else 12):
             log = f"./log/FS-OSD-order-{order}.txt"
             if os.path.exists(log):
                 os.remove(log)

@@ -100,14 +100,16 @@ def test_fs_kernel_matches_reference_policy(handle, golden_dir):
 
     g = load(golden_dir, "fs_ref_shim.npz")
     G = load(golden_dir, "code_ref.npz")["G"].astype(np.int64)
-    for order in (1, 2):
+    for order in (1, 2, 3):  # 3 = the reference's default order_limit; its golden covers the first 12 frames
         GL.set_map("order_limit", order)
-        seq = F.generate_sequential_teps(64, order)
-        assert np.array_equal(np.concatenate(seq, 0), np.unpackbits(g[f"seq{order}"], axis=1)[:, :64])
-        res = F.fs_osd_batch(g["y"], g["labels"], order, float(g["beta"]))
+        n = len(g[f"success{order}"])
+        if order < 3:
+            seq = F.generate_sequential_teps(64, order)
+            assert np.array_equal(np.concatenate(seq, 0), np.unpackbits(g[f"seq{order}"], axis=1)[:, :64])
+        res = F.fs_osd_batch(g["y"][:n], g["labels"][:n], order, float(g["beta"]))
         assert np.array_equal(res["correct"].astype(int), g[f"success{order}"])   # the reference's own S/F per frame
         assert np.array_equal(res["num_teps"], g[f"num_teps{order}"])             # and its TEP counts
-        for i in range(len(g["y"])):
+        for i in range(n if order < 3 else 4):
             ref = OO.fs_frame(g["y"][i], G, order, 6.5, 30, 0.1)
             assert np.array_equal(res["codeword"][i], ref["codeword"])
             assert (int(res["best_tep"][i]), int(res["num_teps"][i]), int(res["stop_kind"][i])) == (ref["best_tep"], ref["num_teps"], ref["stop_kind"])

@@ -195,3 +195,30 @@ def test_quantize_is_exact_and_scale_invariant():
     assert np.array_equal(np.ldexp(q[big].astype(np.float64), E - 54), np.abs(y[big]).astype(np.float64))
     q2, E2 = OO.quantize(y * np.float32(1024))
     assert np.array_equal(q, q2) and E2 == E + 10
+
+
+def test_fs_policy_oracle_equals_reference_outcomes(golden_dir):
+    """oracle fs_frame vs the reference's own fs_osd run under the TF shim: per-frame S/F and TEP counts, at
+    order_limit 1, 2 and (first frames) 3, the reference's default."""
+    g = load(golden_dir, "fs_ref_shim.npz")
+    G = load(golden_dir, "code_ref.npz")["G"].astype(np.int64)
+    for order, n in ((1, len(g["y"])), (2, len(g["y"])), (3, 6)):
+        for i in range(n):
+            r = OO.fs_frame(g["y"][i], G, order, 6.5, int(g["tau_psc"]), float(g["beta"]), labels=g["labels"][i])
+            assert int(r["success"]) == int(g[f"success{order}"][i]), (order, i)
+            assert r["num_teps"] == int(g[f"num_teps{order}"][i]), (order, i)
+
+
+def test_pb_policy_oracle_equals_reference_outcomes(golden_dir):
+    """oracle pb_frame vs the reference's own pb_osd under the TF shim: S/F, TEPs visited, both improvement counters
+    and the list-comparison count per frame, at order_limit 1, 2 and 3 (the reference's default)."""
+    from oracle import pb_oracle as PB
+
+    g = load(golden_dir, "pb_ref_shim.npz")
+    G = load(golden_dir, "code_ref.npz")["G"].astype(np.int64)
+    for order, snr, tag in ((1, 2.5, "o1_snr25"), (2, 2.5, "o2_snr25"), (2, 3.5, "o2_snr35"), (3, 2.5, "o3_snr25")):
+        for i in range(len(g["y"])):
+            r = PB.pb_frame(g["y"][i], G, snr, order, labels=g["labels"][i])
+            got = (int(r["success"]), r["num_teps"], r["suc1"], r["suc2"], r["list_cmp"])
+            want = tuple(int(g[f"{k}_{tag}"][i]) for k in ("success", "num_teps", "suc1", "suc2", "list_cmp"))
+            assert got == want, (tag, i, got, want)
