@@ -117,10 +117,10 @@ class Decoding_model:
             traj = np.empty((len(idx), L.num_iterations + 1, 128), np.float32)
             bits = np.empty((len(idx), 4), np.uint32)
             h.call("ldpcb_nms_decode_host", yf, len(idx), L.num_iterations, alpha, w_vc, w_marg, 0, bits, None, None, traj)
-            for n, i in enumerate(idx):
-                for j in range(L.num_iterations + 1):
-                    buffer_inputs.append(traj[n, j])
-                    buffer_labels.append(lab[i])
+            # the reference's layout (ms_test.py:60-63): for each failure its 13 rows, the label repeated 13 times
+            rows = L.num_iterations + 1
+            buffer_inputs = list(traj.reshape(-1, traj.shape[-1]))
+            buffer_labels = list(np.repeat(lab[idx], rows, axis=0))
         return buffer_inputs, buffer_labels
 
     def get_eval(self, soft_output_list, labels):
