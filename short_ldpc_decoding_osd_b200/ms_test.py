@@ -120,7 +120,7 @@ class Decoding_model:
             # the reference's layout (ms_test.py:60-63): for each failure its 13 rows, the label repeated 13 times
             rows = L.num_iterations + 1
             buffer_inputs = list(traj.reshape(-1, traj.shape[-1]))
-            buffer_labels = list(np.repeat(lab[idx], rows, axis=0))
+            buffer_labels = [r for r in lab[idx] for _ in range(rows)]  # 13 references to one row, no copies
         return buffer_inputs, buffer_labels
 
     def get_eval(self, soft_output_list, labels):
