@@ -40,7 +40,7 @@ print('simulate order 2', t, 'frames/s %.3e' % (B / t[0] * 1e3))
 nt = torch.empty(Bo, dtype=torch.int32, device='cuda'); sk = torch.empty(Bo, dtype=torch.uint8, device='cuda')
 fails_idx = syn.bool().nonzero().flatten()[:Bo]
 yf = y[fails_idx].contiguous(); Bf = yf.shape[0]
-for order in (1, 2):
+for order in (1, 2, 3):
     t = timeit(lambda: h.call('ldpcb_osd_fs_decode', yf, Bf, order, 6.5, 30, 6.4, bits, None, nt, sk, None, None, None, None), n=3, warm=1)
     print('fs-osd order', order, t, 'frames/s %.3e' % (Bf / t[0] * 1e3), 'avg teps %.1f' % nt[:Bf].float().mean().item())
 st4 = torch.empty((Bf, 4), dtype=torch.int32, device='cuda')
