@@ -1,7 +1,7 @@
 // Ordered-statistics decoding.  One CTA of four warps works on four frames at a time: each warp
 // prepares one frame (sort, elimination, P' rows, exact reliabilities), then the four warps sweep the
-// TEP list of each prepared frame together through one shared 16 KB weighted-popcount table.
-// Everything stays on chip between the 512-byte LLR load and the 16-byte codeword store.
+// TEP list of each prepared frame together.  Everything stays on chip between the 512-byte LLR load and
+// the 16-byte codeword store.
 //
 // Replaces, per frame (reference paths relative to LDPC_128/):
 //   swapped_info           PB_OSD/pb_testing.py:306-320  (reliability sort, pi1)
@@ -10,10 +10,11 @@
 //   convention_osd_main    FS_OSD/convention_osd.py:49-77 (TEP sweep, re-encode, discrepancy, argmin)
 //   osd.acquire_min        DL_OSD_Testing_serial/ordered_statistics_decoding.py:153-162 (block minima)
 //
-// Prepare (one warp, one frame):
-//   1. bitonic sort of the 128 keys |y| (raw bits) with the index as payload, four keys per lane.
-//      The network is not stable, so a frame that contains two equal keys (2.7e-4 of AWGN frames,
-//      every frame of a quantised input) is re-ranked by an exact rank sort with tf.argsort's tie rule.
+// Prepare (one warp, one frame; osd_prepare.cuh):
+//   1. bitonic sort of the 128 keys |y|, four per lane, on single words (key bits with the index in the low 7
+//      bits); a frame in which two keys agree in their upper 24 bits is re-sorted with (key, index) pairs, and
+//      one with two equal keys (2.7e-4 of AWGN frames, every frame of a quantised input) is re-ranked by an
+//      exact rank sort with tf.argsort's tie rule.
 //   2. column-major GF(2) elimination of G[:, pi1]: lane l holds sorted columns 4l..4l+3 as 64-bit
 //      words (bit r = row r); columns are scanned most reliable first, a column with a 1 in a row not
 //      yet used becomes the next pivot (greedy most-reliable basis).  The reference's rule (row swap /
@@ -22,10 +23,13 @@
 //      the argument, tests compare with the reference's own full_gf2elim.
 //   3. P' rows: 64x64 bit transpose of the non-pivot columns (four 32x32 warp butterflies)
 //   4. exact integer reliabilities q = rint(|y| * 2^(54-E)); order-0 codeword; per-position deltas
-// Sweep (four warps, one frame at a time):
-//   5. byte LUTs of the 64 LRB weights; for TEP i: D = d0 ^ XOR_{t in TEP} P'_t,
-//      score = base + sum delta_t + sum_b LUT_b[byte_b(D)]
-//   6. lexicographic (score, index) minimum = first minimum in enumeration order (tf.argmin)
+// Sweep (four warps, one frame at a time): for TEP i, D = d0 ^ XOR_{t in TEP} P'_t and
+// score = base + sum delta_t + W(D), W the weighted popcount over the 64 LRB reliabilities.
+//   5a. orders 0, 1, 3: truncated 32-bit scores through thirteen 5-bit tables held one entry per lane (shuffles)
+//   5b. order 2: the tensor-core pair sweep below (IMMA over masked weight byte planes)
+//   5c. block minima (DL path), FS policy and the near-tie fallback: exact 64-bit scores through byte LUTs
+//   6. the TEPs within the truncation window of the minimum are re-scored exactly; lexicographic
+//      (score, index) minimum = first minimum in enumeration order (tf.argmin)
 #include "common.cuh"
 #include "osd_prepare.cuh"
 
