@@ -55,7 +55,7 @@ struct TepTable {
     std::vector<uint32_t> host;
     int n = 0;
     int maxw = 0;
-    // order 2 only: inverse of the enumeration, [i*64+j] (i<j) -> index of the pair TEP, [4096+i] -> index of the
+    // orders 0..2: inverse of the enumeration, [i*64+j] (i<j) -> index of the pair TEP, [4096+i] -> index of the
     // single TEP {i}, [4096+64] -> index of the empty TEP (the tensor-core pair sweep visits TEPs in its own order)
     uint16_t* pair_dev = nullptr;
 };
@@ -133,7 +133,7 @@ struct OsdArgs {
     const uint32_t* teps;
     int n_teps;
     int maxw;
-    const uint16_t* pair_index;  // optional (full order-2 tables): selects the tensor-core pair sweep
+    const uint16_t* pair_index;  // optional (full order-0/1/2 tables): selects the warp-local sweep (orders 0, 1) or the tensor-core pair sweep (order 2)
     const int32_t* block_start;  // NULL => one block [0,n_teps)
     int n_blocks;
     int flags;

@@ -109,7 +109,7 @@ int build_tep_tables(ldpcb_handle* h) {
             padded.resize(t.n + 128, 0xFFFFFFFFu);
             LDPCB_CUDA(h, cudaMalloc(&t.dev, sizeof(uint32_t) * padded.size()));
             LDPCB_CUDA(h, cudaMemcpy(t.dev, padded.data(), sizeof(uint32_t) * padded.size(), cudaMemcpyHostToDevice));
-            if (order == 2) {
+            if (order <= 2) {
                 std::vector<uint16_t> inv(OSD_PAIR_TABLE, 0xFFFFu);
                 for (int i = 0; i < t.n; ++i) {
                     const uint32_t v = t.host[i];

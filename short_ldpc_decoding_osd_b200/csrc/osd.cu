@@ -127,14 +127,16 @@ __device__ __forceinline__ void track2(int& s0, int& s1, int p) {
     s0 = min(s0, p);
 }
 
-template <int MAXW, bool BLOCKS, bool PAIR>
-__global__ void __launch_bounds__(OSD_THREADS, PAIR ? 6 : 6) osd_kernel(OsdArgs a, const uint64_t* __restrict__ gcol) {
+// SOLO (full order-0/1 lists): every warp sweeps its own frame -- 65 TEPs are three per lane -- so the CTA needs no
+// barrier, no LUT and no table in shared memory (the dynamic shared memory then holds the four FrameSm only).
+template <int MAXW, bool BLOCKS, bool PAIR, bool SOLO>
+__global__ void __launch_bounds__(OSD_THREADS, 6) osd_kernel(OsdArgs a, const uint64_t* __restrict__ gcol) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    OsdSmem& S = *reinterpret_cast<OsdSmem*>(smem_raw);
+    OsdSmem& S = *reinterpret_cast<OsdSmem*>(smem_raw);  // not touched when SOLO
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    FrameSm& F = S.fr[warp];
+    FrameSm& F = SOLO ? reinterpret_cast<FrameSm*>(smem_raw)[warp] : S.fr[warp];
     const int64_t nframes = a.count ? (int64_t)*a.count : a.B;
     const bool ties_high = (a.flags & LDPCB_OSD_TIES_HIGH_INDEX_FIRST) != 0;
     const bool disc_from_score = (a.flags & LDPCB_OSD_DISC_HARD_FROM_SCORE) != 0;
@@ -151,8 +153,10 @@ __global__ void __launch_bounds__(OSD_THREADS, PAIR ? 6 : 6) osd_kernel(OsdArgs 
         const int E = P.E;
         // ---- 5./6. sweep: the four warps take the prepared frames in turn -------------------------------------
         int sp0 = 0x7fffffff, sp1 = 0x7fffffff, spz = 0x7fffffff;  // pair sweep: packed scores of this lane's single TEPs and of the empty TEP
+        long long solo_s = 0x7fffffffffffffffll;
+        int solo_i = 0x7fffffff;
         if (!BLOCKS && active) {
-            if (lane == 0) { S.cand_n[warp] = 0; S.cand_ovf[warp] = 0; }
+            if (!SOLO && lane == 0) { S.cand_n[warp] = 0; S.cand_ovf[warp] = 0; }
             __syncwarp();
             // 5-bit chunk tables of the 32-bit LRB weights: tabs[j][e] = sum of w32[5j+i] over the set bits i of e
             int tb[13];
@@ -172,10 +176,41 @@ __global__ void __launch_bounds__(OSD_THREADS, PAIR ? 6 : 6) osd_kernel(OsdArgs 
                         tb[pos / 5] += (int)(lb[pos % 5] * ww[u]);
                     }
                 }
-                if (!PAIR) {
+                if (!PAIR && !SOLO) {
 #pragma unroll
                     for (int j = 0; j < 13; ++j) S.tabs[warp][j][lane] = tb[j];
                 }
+            }
+            if (SOLO) {
+                // truncated scores of the empty TEP and of this lane's two single TEPs, warp minimum, then the exact
+                // score of everything inside the truncation window (almost always one TEP)
+                const int b32 = F.base32;
+                const int s_z = b32 + wpop_shfl(tb, d0);
+                int s_a = b32 + F.qd32[lane] + wpop_shfl(tb, d0 ^ myprow[0]);
+                int s_b = b32 + F.qd32[lane + 32] + wpop_shfl(tb, d0 ^ myprow[1]);
+                if (a.n_teps == 1) s_a = s_b = 0x7fffffff;  // order 0
+                int m = min(min(s_a, s_b), s_z);
+#pragma unroll
+                for (int x = 16; x; x >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, x));
+                const int lim = m + OSD_WIN;
+                const bool cz = s_z <= lim;
+                unsigned ma = __ballot_sync(0xffffffffu, s_a <= lim), mb = __ballot_sync(0xffffffffu, s_b <= lim);
+                const int nc = (cz ? 1 : 0) + __popc(ma) + __popc(mb);
+                const bool exact = nc > 1 || a.best_score_q != nullptr;
+                const long long q_l0 = (long long)F.qlrb[lane], q_l1 = (long long)F.qlrb[lane + 32];
+                auto consider = [&](int t) {  // t = MRB position of the single TEP, K = the empty TEP
+                    const int ci = (int)a.pair_index[K * K + t];
+                    long long sc = 0;
+                    if (exact) {
+                        const unsigned long long D = d0 ^ F.prow[t];  // prow[K] = 0
+                        const long long sl = (((D >> lane) & 1ull) ? q_l0 : 0ll) + (((D >> (lane + 32)) & 1ull) ? q_l1 : 0ll);
+                        sc = F.base + F.qd[t] + warp_sum_ll(sl);       // qd[K] = 0
+                    }
+                    if (sc < solo_s || (sc == solo_s && ci < solo_i)) { solo_s = sc; solo_i = ci; }
+                };
+                if (cz) consider(K);
+                while (ma) { const int t = __ffs(ma) - 1; ma &= ma - 1; consider(t); }
+                while (mb) { const int t = __ffs(mb) - 1; mb &= mb - 1; consider(t + 32); }
             }
             if (PAIR) {
                 const int qa = F.qd32[lane], qb = F.qd32[lane + 32], b32 = F.base32;
@@ -197,7 +232,7 @@ __global__ void __launch_bounds__(OSD_THREADS, PAIR ? 6 : 6) osd_kernel(OsdArgs 
                 spz = (z << 5) | PAIR_CODE_EMPTY;
             }
         }
-        const int nfr = (int)((nframes - f0) < OSD_FPB ? (nframes - f0) : OSD_FPB);
+        const int nfr = SOLO ? 0 : (int)((nframes - f0) < OSD_FPB ? (nframes - f0) : OSD_FPB);
         for (int w = 0; w < nfr; ++w) {
             const FrameSm& G = S.fr[w];
             __syncthreads();  // (A) frame w prepared; reduction slots and LUT free
@@ -401,14 +436,17 @@ __global__ void __launch_bounds__(OSD_THREADS, PAIR ? 6 : 6) osd_kernel(OsdArgs 
                 }
             }
         }
-        __syncthreads();  // all partial minima written; all LUT reads done
+        if (!SOLO) __syncthreads();  // all partial minima written; all LUT reads done
         // ---- outputs (each warp finishes its own frame) ---------------------------------------------------
         if (active) {
             if (!BLOCKS) {
                 long long best_s = 0x7fffffffffffffffll;
                 int best_i = 0x7fffffff;
-                const int nc = S.cand_n[warp];
-                if (S.cand_ovf[warp] || nc > OSD_CAND_CAP) {
+                const int nc = SOLO ? 0 : S.cand_n[warp];
+                if (SOLO) {
+                    best_s = solo_s;
+                    best_i = solo_i;
+                } else if (S.cand_ovf[warp] || nc > OSD_CAND_CAP) {
                     best_s = S.red_s[warp][0];
                     best_i = S.red_i[warp][0];
 #pragma unroll
@@ -682,11 +720,11 @@ int launch_osd_fs(ldpcb_handle* h, const OsdArgs& a, const FsParams& fp, cudaStr
     return LDPCB_OK;
 }
 
-template <int MAXW, bool BLOCKS, bool PAIR = false>
+template <int MAXW, bool BLOCKS, bool PAIR = false, bool SOLO = false>
 static int launch_variant(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st) {
-    auto kern = osd_kernel<MAXW, BLOCKS, PAIR>;
+    auto kern = osd_kernel<MAXW, BLOCKS, PAIR, SOLO>;
     static_assert(offsetof(OsdSmem, tabs) == OSD_SMEM_NO_TABS, "OsdSmem layout changed");
-    const int smem = PAIR ? OSD_SMEM_NO_TABS : (int)sizeof(OsdSmem);
+    const int smem = SOLO ? OSD_FPB * (int)sizeof(FrameSm) : (PAIR ? OSD_SMEM_NO_TABS : (int)sizeof(OsdSmem));
     static thread_local int occ_cache[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int& occ = occ_cache[h->device & 7];
     if (occ == 0) {
@@ -707,7 +745,9 @@ int launch_osd(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st) {
     if (a.B == 0) return LDPCB_OK;
     const bool blocks = a.block_start != nullptr;
     switch (a.maxw) {
-        case 1: return blocks ? launch_variant<1, true>(h, a, st) : launch_variant<1, false>(h, a, st);
+        case 1:
+            if (blocks) return launch_variant<1, true>(h, a, st);
+            return (a.pair_index && (a.n_teps == 1 || a.n_teps == 65)) ? launch_variant<1, false, false, true>(h, a, st) : launch_variant<1, false>(h, a, st);
         case 2:
             if (blocks) return launch_variant<2, true>(h, a, st);
             return (a.pair_index && a.n_teps == 2081) ? launch_variant<2, false, true>(h, a, st) : launch_variant<2, false>(h, a, st);
