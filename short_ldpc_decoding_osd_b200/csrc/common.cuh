@@ -149,6 +149,7 @@ struct OsdArgs {
     int64_t* truth_score_q;
 };
 int launch_osd(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st);
+int launch_osd_pair(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st);  // order 2, full lists: warp-local tensor-core pair sweep
 
 // FS-OSD policy parameters (FS_OSD/fs_testing.py:92,129-160)
 struct FsParams {

@@ -30,102 +30,13 @@
 //   5c. block minima (DL path), FS policy and the near-tie fallback: exact 64-bit scores through byte LUTs
 //   6. the TEPs within the truncation window of the minimum are re-scored exactly; lexicographic
 //      (score, index) minimum = first minimum in enumeration order (tf.argmin)
+#include <cstdlib>
+
 #include "common.cuh"
 #include "osd_prepare.cuh"
+#include "osd_sweep.cuh"
 
 namespace ldpcb {
-
-constexpr int OSD_WIN = 72;       // >= 64 LRB terms + 4 MRB terms + 1 base term
-constexpr int OSD_CAND_CAP = 16;
-
-// lut[b][x] = sum of q_lrb[8b+i] over the set bits i of x; thread: table b, low nibble fixed
-__device__ __forceinline__ void build_lut64(OsdSmem& S, const FrameSm& G, int tid) {
-    const int b = tid >> 4, lo = tid & 15;
-    unsigned long long wv[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) wv[i] = G.qlrb[8 * b + i];
-    unsigned long long lsum = 0ull;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) lsum += ((lo >> i) & 1) ? wv[i] : 0ull;
-    unsigned long long e[16];
-    e[0] = lsum;
-#pragma unroll
-    for (int x = 1; x < 16; ++x) e[x] = e[x & (x - 1)] + wv[4 + (31 - __clz(x & -x))];
-#pragma unroll
-    for (int x = 0; x < 16; ++x) S.lut[b][x * 16 + lo] = e[x];
-}
-
-// exact score of one TEP through the byte LUTs
-template <int MAXW>
-__device__ __forceinline__ long long score64(const OsdSmem& S, const FrameSm& G, unsigned tw) {
-    unsigned long long D = G.d0;
-    long long s = G.base;
-#pragma unroll
-    for (int j = 0; j < MAXW; ++j) {
-        const unsigned t = min((tw >> (8 * j)) & 0xffu, 64u);
-        D ^= G.prow[t];
-        s += G.qd[t];
-    }
-#pragma unroll
-    for (int b = 0; b < 8; ++b) s += (long long)S.lut[b][(unsigned)(D >> (8 * b)) & 0xffu];
-    return s;
-}
-
-// ---- tensor-core pair sweep (full order-2 lists) ------------------------------------------------------------------
-// With u_i = d0 ^ P'_i the truncated score of the pair TEP {i, j} is
-//     S(i,j) = R_i + C_j - 2 * M[i][j],   R_i = base + qd_i + W(u_i)  (= score of the single TEP {i}),
-//     C_j = qd_j + W(P'_j),               M[i][j] = sum_l w_l * u_i[l] * P'_j[l]
-// (W(x ^ y) = W(x) + W(y) - 2 W(x & y) for a weighted popcount W).  M is a 64x64x64 integer matrix product per
-// frame: A[i][l] = w_l masked by bit l of u_i, split into two byte planes (w < 2^16), B[l][j] = bit l of P'_j, both
-// u8, accumulated in s32 by mma.sync m16n8k32 (IMMA.16832.U8.U8).  Only the 20 of the 32 16x8 tiles that contain a
-// pair i < j are computed, five per warp.  The 129 values R, C and the empty TEP's score come from the owner warp's
-// 5-bit shuffle tables.  Scores are packed as (S << 5) | code (code = tile and element, or a single / the empty
-// TEP), so a thread tracks its minimum and second minimum with three integer min/max per element; the candidates
-// within the truncation window of the CTA-wide minimum are re-scored exactly as in the generic sweep.
-constexpr int PAIR_SH = 38;  // w = floor(q / 2^38) < 2^16: two byte planes; window = 72 * 2^38 ~ 2^-9 of the largest |y|
-constexpr int PAIR_CODE_SINGLE = 28, PAIR_CODE_EMPTY = 30;
-__constant__ unsigned char c_pair_tiles[OSD_FPB][5][2] = {  // [warp][turn] -> (16-row block of i, 8-column block of j)
-    {{0, 0}, {0, 1}, {0, 2}, {0, 3}, {0, 4}},
-    {{0, 5}, {0, 6}, {0, 7}, {1, 2}, {1, 3}},
-    {{1, 4}, {1, 5}, {1, 6}, {1, 7}, {2, 4}},
-    {{2, 5}, {2, 6}, {2, 7}, {3, 6}, {3, 7}}};
-
-__device__ __forceinline__ void imma_u8(int (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
-    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-// four bits -> four bytes of 0/1 (bit k of the nibble in byte k)
-__device__ __forceinline__ unsigned spread4(unsigned word, int sh) { return (((word >> sh) & 0xFu) * 0x00204081u) & 0x01010101u; }
-// four bits -> four bytes of 0x00/0xFF: the bits are moved to the byte sign positions and replicated by PRMT
-__device__ __forceinline__ unsigned mask4(unsigned word, int sh) {
-    const unsigned x = ((word >> sh) & 0xFu) * 0x10204080u;
-    unsigned r;
-    asm("prmt.b32 %0, %1, 0, 0xba98;" : "=r"(r) : "r"(x));  // selector nibble 8+k: replicate the sign of byte k
-    return r;
-}
-// weighted popcount of D through the thirteen 5-bit tables held one entry per lane
-__device__ __forceinline__ int wpop_shfl(const int (&tb)[13], unsigned long long D) {
-    const unsigned lo = (unsigned)D, hi = (unsigned)(D >> 32);
-    int s = __shfl_sync(0xffffffffu, tb[0], lo);  // the source lane is taken modulo 32
-    s += __shfl_sync(0xffffffffu, tb[1], lo >> 5);
-    s += __shfl_sync(0xffffffffu, tb[2], lo >> 10);
-    s += __shfl_sync(0xffffffffu, tb[3], lo >> 15);
-    s += __shfl_sync(0xffffffffu, tb[4], lo >> 20);
-    s += __shfl_sync(0xffffffffu, tb[5], lo >> 25);
-    s += __shfl_sync(0xffffffffu, tb[6], (unsigned)(D >> 30));
-    s += __shfl_sync(0xffffffffu, tb[7], hi >> 3);
-    s += __shfl_sync(0xffffffffu, tb[8], hi >> 8);
-    s += __shfl_sync(0xffffffffu, tb[9], hi >> 13);
-    s += __shfl_sync(0xffffffffu, tb[10], hi >> 18);
-    s += __shfl_sync(0xffffffffu, tb[11], hi >> 23);
-    s += __shfl_sync(0xffffffffu, tb[12], hi >> 28);
-    return s;
-}
-__device__ __forceinline__ void track2(int& s0, int& s1, int p) {
-    s1 = min(s1, max(p, s0));
-    s0 = min(s0, p);
-}
 
 // SOLO (full order-0/1 lists): every warp sweeps its own frame -- 65 TEPs are three per lane -- so the CTA needs no
 // barrier, no LUT and no table in shared memory (the dynamic shared memory then holds the four FrameSm only).
@@ -160,22 +71,8 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_kernel(OsdArgs a, const ui
             __syncwarp();
             // 5-bit chunk tables of the 32-bit LRB weights: tabs[j][e] = sum of w32[5j+i] over the set bits i of e
             int tb[13];
+            build_shfl_tables(F, lane, tb);
             {
-                unsigned lb[5];
-#pragma unroll
-                for (int i = 0; i < 5; ++i) lb[i] = (lane >> i) & 1u;
-#pragma unroll
-                for (int j = 0; j < 13; ++j) tb[j] = 0;
-#pragma unroll
-                for (int v4 = 0; v4 < 16; ++v4) {  // four weights per (broadcast) load, one multiply-add per term
-                    const uint4 wv = reinterpret_cast<const uint4*>(F.w32)[v4];
-                    const unsigned ww[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int pos = 4 * v4 + u;
-                        tb[pos / 5] += (int)(lb[pos % 5] * ww[u]);
-                    }
-                }
                 if (!PAIR && !SOLO) {
 #pragma unroll
                     for (int j = 0; j < 13; ++j) S.tabs[warp][j][lane] = tb[j];
@@ -330,12 +227,12 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_kernel(OsdArgs a, const ui
                 if (s1 <= lim) S.cand_ovf[w] = 1;  // a second candidate of this thread: take the exact path
                 __syncthreads();  // (C)
                 if (S.cand_ovf[w] || S.cand_n[w] > OSD_CAND_CAP) {
-                    build_lut64(S, G, tid);
+                    build_lut64(S.lut, G, tid);
                     __syncthreads();
                     long long bs = 0x7fffffffffffffffll;
                     int bi = 0x7fffffff;
                     for (int i = tid; i < a.n_teps; i += OSD_THREADS) {
-                        const long long s = score64<MAXW>(S, G, __ldg(a.teps + i));
+                        const long long s = score64<MAXW>(S.lut, G, __ldg(a.teps + i));
                         if (s < bs) { bs = s; bi = i; }
                     }
                     warp_argmin(bs, bi);
@@ -404,19 +301,19 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_kernel(OsdArgs a, const ui
                 __syncthreads();  // (C)
                 if (S.cand_ovf[w] || S.cand_n[w] > OSD_CAND_CAP) {
                     // too many near-ties (e.g. quantised inputs): exact 64-bit sweep through the byte LUTs
-                    build_lut64(S, G, tid);
+                    build_lut64(S.lut, G, tid);
                     __syncthreads();
                     long long bs = 0x7fffffffffffffffll;
                     int bi = 0x7fffffff;
                     for (int i = tid; i < a.n_teps; i += OSD_THREADS) {
-                        const long long s = score64<MAXW>(S, G, __ldg(a.teps + i));
+                        const long long s = score64<MAXW>(S.lut, G, __ldg(a.teps + i));
                         if (s < bs) { bs = s; bi = i; }
                     }
                     warp_argmin(bs, bi);
                     if (lane == 0) { S.red_s[w][warp] = bs; S.red_i[w][warp] = bi; }
                 }
             } else {
-                build_lut64(S, G, tid);
+                build_lut64(S.lut, G, tid);
                 __syncthreads();
                 // block minima: warp v takes blocks v, v+4, ... of this frame
                 const int64_t fw = f0 + w;
@@ -425,7 +322,7 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_kernel(OsdArgs a, const ui
                     long long bs = 0x7fffffffffffffffll;
                     int bi = 0x7fffffff;
                     for (int i = i0 + lane; i < i1; i += 32) {
-                        const long long s = score64<MAXW>(S, G, __ldg(a.teps + i));
+                        const long long s = score64<MAXW>(S.lut, G, __ldg(a.teps + i));
                         if (s < bs) { bs = s; bi = i; }
                     }
                     warp_argmin(bs, bi);
@@ -750,7 +647,8 @@ int launch_osd(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st) {
             return (a.pair_index && (a.n_teps == 1 || a.n_teps == 65)) ? launch_variant<1, false, false, true>(h, a, st) : launch_variant<1, false>(h, a, st);
         case 2:
             if (blocks) return launch_variant<2, true>(h, a, st);
-            return (a.pair_index && a.n_teps == 2081) ? launch_variant<2, false, true>(h, a, st) : launch_variant<2, false>(h, a, st);
+            if (a.pair_index && a.n_teps == 2081) return getenv("LDPCB_PAIR_CTA") ? launch_variant<2, false, true>(h, a, st) : launch_osd_pair(h, a, st);
+            return launch_variant<2, false>(h, a, st);
         case 3: return blocks ? launch_variant<3, true>(h, a, st) : launch_variant<3, false>(h, a, st);
         default: return blocks ? launch_variant<4, true>(h, a, st) : launch_variant<4, false>(h, a, st);
     }
