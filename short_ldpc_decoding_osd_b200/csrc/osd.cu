@@ -30,8 +30,6 @@
 //   5c. block minima (DL path), FS policy and the near-tie fallback: exact 64-bit scores through byte LUTs
 //   6. the TEPs within the truncation window of the minimum are re-scored exactly; lexicographic
 //      (score, index) minimum = first minimum in enumeration order (tf.argmin)
-#include <cstdlib>
-
 #include "common.cuh"
 #include "osd_prepare.cuh"
 #include "osd_sweep.cuh"
@@ -40,7 +38,7 @@ namespace ldpcb {
 
 // SOLO (full order-0/1 lists): every warp sweeps its own frame -- 65 TEPs are three per lane -- so the CTA needs no
 // barrier, no LUT and no table in shared memory (the dynamic shared memory then holds the four FrameSm only).
-template <int MAXW, bool BLOCKS, bool PAIR, bool SOLO>
+template <int MAXW, bool BLOCKS, bool SOLO>
 __global__ void __launch_bounds__(OSD_THREADS, 6) osd_kernel(OsdArgs a, const uint64_t* __restrict__ gcol) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     OsdSmem& S = *reinterpret_cast<OsdSmem*>(smem_raw);  // not touched when SOLO
@@ -57,13 +55,12 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_kernel(OsdArgs a, const ui
         const bool active = f < nframes;
         const int64_t row = active ? (a.idx ? (int64_t)a.idx[f] : f) : 0;
         Prep P = {};
-        if (active) P = prepare_frame<BLOCKS, PAIR ? PAIR_SH : 30>(a, F, gcol, row, f, lane, ties_high, disc_from_score);
+        if (active) P = prepare_frame<BLOCKS>(a, F, gcol, row, f, lane, ties_high, disc_from_score);
         const unsigned char* pm = P.pm;
         const unsigned long long* myprow = P.myprow;
         const unsigned long long hd_lrb = P.hd_lrb, ho_mrb = P.ho_mrb, d0 = P.d0;
         const int E = P.E;
         // ---- 5./6. sweep: the four warps take the prepared frames in turn -------------------------------------
-        int sp0 = 0x7fffffff, sp1 = 0x7fffffff, spz = 0x7fffffff;  // pair sweep: packed scores of this lane's single TEPs and of the empty TEP
         long long solo_s = 0x7fffffffffffffffll;
         int solo_i = 0x7fffffff;
         if (!BLOCKS && active) {
@@ -73,7 +70,7 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_kernel(OsdArgs a, const ui
             int tb[13];
             build_shfl_tables(F, lane, tb);
             {
-                if (!PAIR && !SOLO) {
+                if (!SOLO) {
 #pragma unroll
                     for (int j = 0; j < 13; ++j) S.tabs[warp][j][lane] = tb[j];
                 }
@@ -109,136 +106,12 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_kernel(OsdArgs a, const ui
                 while (ma) { const int t = __ffs(ma) - 1; ma &= ma - 1; consider(t); }
                 while (mb) { const int t = __ffs(mb) - 1; mb &= mb - 1; consider(t + 32); }
             }
-            if (PAIR) {
-                const int qa = F.qd32[lane], qb = F.qd32[lane + 32], b32 = F.base32;
-                const int z = b32 + wpop_shfl(tb, d0);
-                const int r0 = b32 + qa + wpop_shfl(tb, d0 ^ myprow[0]);
-                const int r1 = b32 + qb + wpop_shfl(tb, d0 ^ myprow[1]);
-                const int c0 = qa + wpop_shfl(tb, myprow[0]);
-                const int c1 = qb + wpop_shfl(tb, myprow[1]);
-                const unsigned wa = F.w32[lane], wb = F.w32[lane + 32];
-                __syncwarp();  // every lane is done with yo/ys: reuse them
-                int* RC = reinterpret_cast<int*>(F.yo);
-                RC[lane] = r0 << 5; RC[lane + 32] = r1 << 5;
-                RC[64 + lane] = c0 << 5; RC[96 + lane] = c1 << 5;
-                unsigned char* wq = reinterpret_cast<unsigned char*>(F.ys);  // [plane][LRB position]
-                wq[lane] = (unsigned char)(wa & 0xffu); wq[lane + 32] = (unsigned char)(wb & 0xffu);
-                wq[64 + lane] = (unsigned char)(wa >> 8); wq[96 + lane] = (unsigned char)(wb >> 8);
-                sp0 = (r0 << 5) | PAIR_CODE_SINGLE;
-                sp1 = (r1 << 5) | (PAIR_CODE_SINGLE + 1);
-                spz = (z << 5) | PAIR_CODE_EMPTY;
-            }
         }
         const int nfr = SOLO ? 0 : (int)((nframes - f0) < OSD_FPB ? (nframes - f0) : OSD_FPB);
         for (int w = 0; w < nfr; ++w) {
             const FrameSm& G = S.fr[w];
             __syncthreads();  // (A) frame w prepared; reduction slots and LUT free
-            if (PAIR) {
-                const int g = lane >> 2, t = lane & 3;
-                const unsigned* wqw = reinterpret_cast<const unsigned*>(G.ys);
-                const int* RC = reinterpret_cast<const int*>(G.yo);
-                unsigned wr[2][2][2];  // [plane][32-bit half of the LRB][16-bit half]: the four weight bytes this thread's k columns need
-#pragma unroll
-                for (int p = 0; p < 2; ++p)
-#pragma unroll
-                    for (int kk = 0; kk < 2; ++kk)
-#pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) wr[p][kk][hh] = wqw[16 * p + 8 * kk + 4 * hh + t];
-                const unsigned long long gd0 = G.d0;
-                int s0 = 0x7fffffff, s1 = 0x7fffffff;
-                if (warp == w) {  // the owner warp brings the singles and the empty TEP
-                    track2(s0, s1, sp0);
-                    track2(s0, s1, sp1);
-                    if (lane == 0) track2(s0, s1, spz);
-                }
-                const int vb = g - 2 * t;  // i - j of element 0 in a tile on the diagonal
-                unsigned afr[2][2][4];     // [k half][plane][fragment register]
-                int rr[2] = {0, 0};
-                int cur_mi = -1;
-#pragma unroll
-                for (int tt = 0; tt < 5; ++tt) {
-                    const int mi = c_pair_tiles[warp][tt][0], nj = c_pair_tiles[warp][tt][1];
-                    if (mi != cur_mi) {  // warp-uniform: masked weights of rows 16mi+g and +8
-                        cur_mi = mi;
-                        const int i0 = 16 * mi + g;
-                        const unsigned long long u0 = gd0 ^ G.prow[i0], u1 = gd0 ^ G.prow[i0 + 8];
-                        rr[0] = RC[i0];
-                        rr[1] = RC[i0 + 8];
-#pragma unroll
-                        for (int kk = 0; kk < 2; ++kk) {
-                            const unsigned w0 = kk ? (unsigned)(u0 >> 32) : (unsigned)u0;
-                            const unsigned w1 = kk ? (unsigned)(u1 >> 32) : (unsigned)u1;
-#pragma unroll
-                            for (int hh = 0; hh < 2; ++hh) {
-                                const unsigned m0 = mask4(w0, 4 * t + 16 * hh);
-                                const unsigned m1 = mask4(w1, 4 * t + 16 * hh);
-#pragma unroll
-                                for (int p = 0; p < 2; ++p) {
-                                    afr[kk][p][2 * hh] = wr[p][kk][hh] & m0;
-                                    afr[kk][p][2 * hh + 1] = wr[p][kk][hh] & m1;
-                                }
-                            }
-                        }
-                    }
-                    const unsigned long long cj = G.prow[8 * nj + g];
-                    unsigned bfr[2][2];
-#pragma unroll
-                    for (int kk = 0; kk < 2; ++kk)
-#pragma unroll
-                        for (int hh = 0; hh < 2; ++hh)
-                            bfr[kk][hh] = spread4(kk ? (unsigned)(cj >> 32) : (unsigned)cj, 4 * t + 16 * hh);
-                    int acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-#pragma unroll
-                    for (int kk = 0; kk < 2; ++kk)
-#pragma unroll
-                        for (int p = 0; p < 2; ++p) imma_u8(acc[p], afr[kk][p], bfr[kk]);
-                    const int2 cc = *reinterpret_cast<const int2*>(RC + 64 + 8 * nj + 2 * t);
-                    const int dlt = 8 * nj - 16 * mi;
-                    const bool diag = dlt < 16;  // the tile straddles the diagonal (warp-uniform)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int rs = e >> 1, cs = e & 1;
-                        const int rc = rr[rs] + (cs ? cc.y : cc.x) + ((tt << 2) | e);
-                        int p = rc - 64 * acc[0][e] - 16384 * acc[1][e];  // ((R + C - 2M) << 5) | code
-                        if (diag && vb + 8 * rs - cs >= dlt) p = 0x7fffffff;  // i >= j
-                        track2(s0, s1, p);
-                    }
-                }
-                int m = s0;
-#pragma unroll
-                for (int x = 16; x; x >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, x));
-                if (lane == 0) S.red32[warp] = m;
-                __syncthreads();  // (B)
-                m = min(min(S.red32[0], S.red32[1]), min(S.red32[2], S.red32[3]));
-                const int lim = (((m >> 5) + OSD_WIN) << 5) | 31;
-                if (s0 <= lim) {
-                    const int code = s0 & 31;
-                    int pi;
-                    if (code < PAIR_CODE_SINGLE) {
-                        const int tt = code >> 2, e = code & 3;
-                        const int i = 16 * c_pair_tiles[warp][tt][0] + g + 8 * (e >> 1), j = 8 * c_pair_tiles[warp][tt][1] + 2 * t + (e & 1);
-                        pi = i * K + j;
-                    } else {
-                        pi = K * K + (code == PAIR_CODE_EMPTY ? K : lane + 32 * (code - PAIR_CODE_SINGLE));
-                    }
-                    const int p = atomicAdd(&S.cand_n[w], 1);
-                    if (p < OSD_CAND_CAP) S.cand_i[w][p] = (int)a.pair_index[pi];
-                }
-                if (s1 <= lim) S.cand_ovf[w] = 1;  // a second candidate of this thread: take the exact path
-                __syncthreads();  // (C)
-                if (S.cand_ovf[w] || S.cand_n[w] > OSD_CAND_CAP) {
-                    build_lut64(S.lut, G, tid);
-                    __syncthreads();
-                    long long bs = 0x7fffffffffffffffll;
-                    int bi = 0x7fffffff;
-                    for (int i = tid; i < a.n_teps; i += OSD_THREADS) {
-                        const long long s = score64<MAXW>(S.lut, G, __ldg(a.teps + i));
-                        if (s < bs) { bs = s; bi = i; }
-                    }
-                    warp_argmin(bs, bi);
-                    if (lane == 0) { S.red_s[w][warp] = bs; S.red_i[w][warp] = bi; }
-                }
-            } else if (!BLOCKS) {
+            if (!BLOCKS) {
                 // Fast sweep on 32-bit truncated scores S32 = sum floor(term / 2^30): the 64 LRB weights are folded
                 // into thirteen 32-entry tables (5 bits of D each) that live in registers, one entry per lane, and
                 // are looked up with warp shuffles -- no shared-memory bank conflicts.  The exact score satisfies
@@ -617,11 +490,10 @@ int launch_osd_fs(ldpcb_handle* h, const OsdArgs& a, const FsParams& fp, cudaStr
     return LDPCB_OK;
 }
 
-template <int MAXW, bool BLOCKS, bool PAIR = false, bool SOLO = false>
+template <int MAXW, bool BLOCKS, bool SOLO = false>
 static int launch_variant(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st) {
-    auto kern = osd_kernel<MAXW, BLOCKS, PAIR, SOLO>;
-    static_assert(offsetof(OsdSmem, tabs) == OSD_SMEM_NO_TABS, "OsdSmem layout changed");
-    const int smem = SOLO ? OSD_FPB * (int)sizeof(FrameSm) : (PAIR ? OSD_SMEM_NO_TABS : (int)sizeof(OsdSmem));
+    auto kern = osd_kernel<MAXW, BLOCKS, SOLO>;
+    const int smem = SOLO ? OSD_FPB * (int)sizeof(FrameSm) : (int)sizeof(OsdSmem);
     static thread_local int occ_cache[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int& occ = occ_cache[h->device & 7];
     if (occ == 0) {
@@ -644,10 +516,10 @@ int launch_osd(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st) {
     switch (a.maxw) {
         case 1:
             if (blocks) return launch_variant<1, true>(h, a, st);
-            return (a.pair_index && (a.n_teps == 1 || a.n_teps == 65)) ? launch_variant<1, false, false, true>(h, a, st) : launch_variant<1, false>(h, a, st);
+            return (a.pair_index && (a.n_teps == 1 || a.n_teps == 65)) ? launch_variant<1, false, true>(h, a, st) : launch_variant<1, false>(h, a, st);
         case 2:
             if (blocks) return launch_variant<2, true>(h, a, st);
-            if (a.pair_index && a.n_teps == 2081) return getenv("LDPCB_PAIR_CTA") ? launch_variant<2, false, true>(h, a, st) : launch_osd_pair(h, a, st);
+            if (a.pair_index && a.n_teps == 2081) return launch_osd_pair(h, a, st);  // osd_pair.cu
             return launch_variant<2, false>(h, a, st);
         case 3: return blocks ? launch_variant<3, true>(h, a, st) : launch_variant<3, false>(h, a, st);
         default: return blocks ? launch_variant<4, true>(h, a, st) : launch_variant<4, false>(h, a, st);

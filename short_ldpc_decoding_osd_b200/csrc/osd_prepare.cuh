@@ -40,11 +40,8 @@ struct __align__(16) OsdSmem {
     int red_stop[OSD_FPB];           // FS: per-warp first stopping TEP index
     long long fs_score[OSD_FPB];     // FS results per frame
     int fs_opt[OSD_FPB], fs_num[OSD_FPB], fs_kind[OSD_FPB];
-    int tabs[OSD_FPB][13][32];       // fast sweep: 5-bit chunk tables of each frame (entry = lane); last member: the
-                                     // pair sweep keeps its tables in registers and is launched without this part
+    int tabs[OSD_FPB][13][32];       // fast sweep: 5-bit chunk tables of each frame (entry = lane)
 };
-constexpr int OSD_SMEM_NO_TABS = 16384 + OSD_FPB * (int)sizeof(FrameSm) + 8 * OSD_FPB * OSD_FPB + 4 * OSD_FPB * OSD_FPB + 3 * 4 * OSD_FPB +
-                                 4 * OSD_FPB * 16 + 4 * OSD_FPB + 8 * OSD_FPB + 3 * 4 * OSD_FPB;
 
 __device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) {
     unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src);

@@ -48,18 +48,11 @@ __device__ __forceinline__ long long score64(const unsigned long long (*lut)[256
 // (W(x ^ y) = W(x) + W(y) - 2 W(x & y) for a weighted popcount W).  M is a 64x64x64 integer matrix product per
 // frame: A[i][l] = w_l masked by bit l of u_i, split into two byte planes (w < 2^16), B[l][j] = bit l of P'_j, both
 // u8, accumulated in s32 by mma.sync m16n8k32 (IMMA.16832.U8.U8).  Only the 20 of the 32 16x8 tiles that contain a
-// pair i < j are computed, five per warp.  The 129 values R, C and the empty TEP's score come from the owner warp's
-// 5-bit shuffle tables.  Scores are packed as (S << 5) | code (code = tile and element, or a single / the empty
-// TEP), so a thread tracks its minimum and second minimum with three integer min/max per element; the candidates
-// within the truncation window of the CTA-wide minimum are re-scored exactly as in the generic sweep.
+// pair i < j are computed.  The 129 values R, C and the empty TEP's score come from the warp's 5-bit shuffle
+// tables.  Scores are packed as (S << 7) | code (code = tile and element, or a single / the empty TEP), so a thread
+// tracks its minimum and second minimum with three integer min/max per element; the candidates within the
+// truncation window of the minimum are re-scored exactly as in the generic sweep (kernel: osd_pair.cu).
 constexpr int PAIR_SH = 38;  // w = floor(q / 2^38) < 2^16: two byte planes; window = 72 * 2^38 ~ 2^-9 of the largest |y|
-constexpr int PAIR_CODE_SINGLE = 28, PAIR_CODE_EMPTY = 30;
-static __constant__ unsigned char c_pair_tiles[OSD_FPB][5][2] = {  // [warp][turn] -> (16-row block of i, 8-column block of j)
-    {{0, 0}, {0, 1}, {0, 2}, {0, 3}, {0, 4}},
-    {{0, 5}, {0, 6}, {0, 7}, {1, 2}, {1, 3}},
-    {{1, 4}, {1, 5}, {1, 6}, {1, 7}, {2, 4}},
-    {{2, 5}, {2, 6}, {2, 7}, {3, 6}, {3, 7}}};
-
 __device__ __forceinline__ void imma_u8(int (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
     asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
