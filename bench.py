@@ -284,7 +284,7 @@ def run_ours(args):
                 "peak_warp_instr_per_s": issue_peak, "frac": rate / issue_peak}
 
     roofline = {
-        "bound": "hbm", "kernel": "osd_kernel<2,false,true> (tensor-core pair sweep)" if dom_is_osd else "nms_kernel<5,3,true,false,false>",
+        "bound": "hbm", "kernel": "osd_pair_kernel (warp-local tensor-core pair sweep)" if dom_is_osd else "nms_kernel<5,3,true,false,false>",
         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
         "traffic": traffic, "traffic_source": "profiles/r01_traffic.json (ncu dram__bytes per frame x frames of this launch)" if traffic else None,
         "peak_source": peak_src, "kernel_ms": dom_ms, "share_of_step": dom_ms / step_ms,
