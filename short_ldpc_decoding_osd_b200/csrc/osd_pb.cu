@@ -15,17 +15,12 @@
 
 namespace ldpcb {
 
-constexpr int PB_MAX_LIST = 2081;   // every non-zero TEP of weight <= 2 is pushed exactly once
-constexpr int PB_GLIST_CAP = 43776;  // order 3: 43,745 TEPs, the list of a warp lives in global memory (L2 in practice)
+// list capacity of a warp when the lists live in global memory (L2 in practice): every non-zero TEP is pushed once
+__host__ __device__ constexpr int pb_glist_cap(int order) { return order >= 3 ? 43776 : (order == 2 ? 2112 : 96); }
 
 struct __align__(16) PbHead {
     FrameSm fr;
     double cdf_p1[66];                 // BinCDF(b; 64, p1)
-};
-struct __align__(16) PbFrameSm {
-    PbHead h;
-    long long lsum[PB_MAX_LIST + 3];   // MRB weight of the live TEPs in insertion order (tombstone = INT64_MAX)
-    unsigned ltep[PB_MAX_LIST + 3];    // packed positions
 };
 
 __constant__ double c_binom64[65];  // C(64, i)
@@ -47,17 +42,18 @@ __device__ __forceinline__ float mean64_pairwise(const float* v, int lane) {
     return __shfl_sync(0xffffffffu, r, 0) * 0.015625f;
 }
 
-// GLIST: the TEP list of each warp is a slice of pp.glist_sum / pp.glist_tep instead of shared memory
-template <bool GLIST>
+// The TEP list of each warp is a slice of pp.glist_sum / pp.glist_tep (global memory, L2-resident in practice): shared
+// memory only holds the prepared frame, so 28 warps per SM are resident instead of the 4 a 25 KB list per warp allowed.
 __global__ void __launch_bounds__(OSD_THREADS) osd_pb_kernel(OsdArgs a, PbParams pp, const uint64_t* __restrict__ gcol) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    PbHead& W = GLIST ? reinterpret_cast<PbHead*>(smem_raw)[warp] : reinterpret_cast<PbFrameSm*>(smem_raw)[warp].h;
-    const int64_t slice = ((int64_t)blockIdx.x * OSD_FPB + warp) * PB_GLIST_CAP;
-    long long* const lsum = GLIST ? pp.glist_sum + slice : reinterpret_cast<PbFrameSm*>(smem_raw)[warp].lsum;
-    unsigned* const ltep = GLIST ? pp.glist_tep + slice : reinterpret_cast<PbFrameSm*>(smem_raw)[warp].ltep;
-    // GLIST: minimum of every 32 consecutive list entries, so that a pop scans nslots/32 values instead of nslots
-    long long* const bmin = GLIST ? pp.glist_bmin + ((int64_t)blockIdx.x * OSD_FPB + warp) * (PB_GLIST_CAP / 32) : nullptr;
+    PbHead& W = reinterpret_cast<PbHead*>(smem_raw)[warp];
+    const int gcap = pb_glist_cap(pp.order);
+    const int64_t slice = ((int64_t)blockIdx.x * OSD_FPB + warp) * gcap;
+    long long* const lsum = pp.glist_sum + slice;
+    unsigned* const ltep = pp.glist_tep + slice;
+    // minimum of every 32 consecutive list entries, so that a pop scans nslots/32 values instead of nslots
+    long long* const bmin = pp.glist_bmin + ((int64_t)blockIdx.x * OSD_FPB + warp) * (gcap / 32);
     auto refresh_block = [&](int b, int n) {  // n = current list length; all lanes
         const int i = b * 32 + lane;
         long long s = i < n ? lsum[i] : 0x7fffffffffffffffll;
@@ -134,7 +130,7 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_pb_kernel(OsdArgs a, PbParams
         if (lane == 0) {
             lsum[0] = F.qd[K - 1];
             ltep[0] = 0xffffff00u | (unsigned)(K - 1);
-            if (GLIST) bmin[0] = F.qd[K - 1];
+            bmin[0] = F.qd[K - 1];
         }
         __syncwarp();
         int cost = 0, early = 0, suc1 = 0, suc2 = 0, list_cmp = 0;
@@ -143,7 +139,7 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_pb_kernel(OsdArgs a, PbParams
             // pop the first minimum
             long long bs = 0x7fffffffffffffffll;
             int bi = 0x7fffffff;
-            if (GLIST) {
+            {
                 // the first block holding the minimum holds the first minimum
                 const int nb = (nslots + 31) >> 5;
                 for (int b = lane; b < nb; b += 32) {
@@ -154,12 +150,6 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_pb_kernel(OsdArgs a, PbParams
                 const int i = bi * 32 + lane;
                 bs = i < nslots ? lsum[i] : 0x7fffffffffffffffll;
                 bi = i;
-                warp_argmin(bs, bi);
-            } else {
-                for (int i = lane; i < nslots; i += 32) {
-                    const long long s = lsum[i];
-                    if (s < bs) { bs = s; bi = i; }
-                }
                 warp_argmin(bs, bi);
             }
             const unsigned tw = ltep[bi];
@@ -198,7 +188,7 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_pb_kernel(OsdArgs a, PbParams
             nslots += add;
             live += add - 1;
             __syncwarp();
-            if (GLIST) {
+            {
                 const int b0 = bi >> 5, b1 = nslots_old >> 5, b2 = (nslots - 1) >> 5;
                 refresh_block(b0, nslots);
                 if (add > 0 && b1 != b0) refresh_block(b1, nslots);
@@ -288,21 +278,20 @@ int launch_osd_pb(ldpcb_handle* h, const OsdArgs& a, const PbParams& pp, cudaStr
         LDPCB_CUDA(h, cudaMemcpyToSymbol(c_binom64, c, sizeof c));
         consts_ready[h->device & 7] = true;
     }
-    if (pp.order >= 3) {
+    {
         // lists in global memory: one slice per resident warp
         const int smem = OSD_FPB * (int)sizeof(PbHead);
         static thread_local int occ_g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         int& occ = occ_g[h->device & 7];
         if (occ == 0) {
-            LDPCB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, osd_pb_kernel<true>, OSD_THREADS, smem));
+            LDPCB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, osd_pb_kernel, OSD_THREADS, smem));
             if (occ < 1) occ = 1;
-            if (occ > 4) occ = 4;  // 16 warps per SM: 148 x 16 x 43,776 x 12 B = 1.2 GB of lists
         }
         int64_t want = (a.B + OSD_FPB - 1) / OSD_FPB;
-        int64_t cap = (int64_t)h->sm_count * occ;
+        int64_t cap = (int64_t)h->sm_count * (pp.order >= 3 && occ > 4 ? 4 : occ);  // order 3: 16 warps per SM = 1.2 GB of lists
         int grid = (int)(want < cap ? want : cap);
         if (grid < 1) grid = 1;
-        const size_t per = (size_t)grid * OSD_FPB * PB_GLIST_CAP;
+        const size_t per = (size_t)grid * OSD_FPB * pb_glist_cap(pp.order);
         if (h->pb_list_cap < per) {
             if (h->pb_list) { LDPCB_CUDA(h, cudaDeviceSynchronize()); LDPCB_CUDA(h, cudaFree(h->pb_list)); h->pb_list = nullptr; h->pb_list_cap = 0; }
             LDPCB_CUDA(h, cudaMalloc(&h->pb_list, per * (sizeof(long long) + sizeof(unsigned)) + per / 32 * sizeof(long long)));
@@ -312,25 +301,10 @@ int launch_osd_pb(ldpcb_handle* h, const OsdArgs& a, const PbParams& pp, cudaStr
         q.glist_sum = reinterpret_cast<long long*>(h->pb_list);
         q.glist_bmin = reinterpret_cast<long long*>(h->pb_list + per * sizeof(long long));
         q.glist_tep = reinterpret_cast<unsigned*>(h->pb_list + per * sizeof(long long) + per / 32 * sizeof(long long));
-        osd_pb_kernel<true><<<grid, OSD_THREADS, smem, st>>>(a, q, h->gcol_dev);
-        LDPCB_LAUNCH_CHECK(h, "osd_pb_kernel<global list>");
+        osd_pb_kernel<<<grid, OSD_THREADS, smem, st>>>(a, q, h->gcol_dev);
+        LDPCB_LAUNCH_CHECK(h, "osd_pb_kernel");
         return LDPCB_OK;
     }
-    const int smem = OSD_FPB * (int)sizeof(PbFrameSm);
-    static thread_local int occ_cache[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int& occ = occ_cache[h->device & 7];
-    if (occ == 0) {
-        LDPCB_CUDA(h, cudaFuncSetAttribute(osd_pb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        LDPCB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, osd_pb_kernel<false>, OSD_THREADS, smem));
-        if (occ < 1) occ = 1;
-    }
-    int64_t want = (a.B + OSD_FPB - 1) / OSD_FPB;
-    int64_t cap = (int64_t)h->sm_count * occ;
-    int grid = (int)(want < cap ? want : cap);
-    if (grid < 1) grid = 1;
-    osd_pb_kernel<false><<<grid, OSD_THREADS, smem, st>>>(a, pp, h->gcol_dev);
-    LDPCB_LAUNCH_CHECK(h, "osd_pb_kernel");
-    return LDPCB_OK;
 }
 
 }  // namespace ldpcb
