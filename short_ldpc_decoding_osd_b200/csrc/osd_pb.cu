@@ -56,12 +56,7 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_pb_kernel(OsdArgs a, PbParams
     long long* const bmin = pp.glist_bmin + ((int64_t)blockIdx.x * OSD_FPB + warp) * (gcap / 32);
     auto refresh_block = [&](int b, int n) {  // n = current list length; all lanes
         const int i = b * 32 + lane;
-        long long s = i < n ? lsum[i] : 0x7fffffffffffffffll;
-#pragma unroll
-        for (int m = 16; m; m >>= 1) {
-            const long long o = (long long)shfl_xor64((unsigned long long)s, m);
-            s = o < s ? o : s;
-        }
+        const long long s = warp_min_ll(i < n ? lsum[i] : 0x7fffffffffffffffll);
         if (lane == 0) bmin[b] = s;
     };
     FrameSm& F = W.fr;
@@ -120,7 +115,7 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_pb_kernel(OsdArgs a, PbParams
 
         auto weighted = [&](unsigned long long D) -> long long {
             const long long s = (((D >> lane) & 1ull) ? q_l0 : 0ll) + (((D >> (lane + 32)) & 1ull) ? q_l1 : 0ll);
-            return warp_sum_ll(s);
+            return warp_sum_nonneg(s);
         };
         const unsigned long long d0 = P.d0;
         long long w_dmin = weighted(d0);

@@ -63,13 +63,29 @@ __device__ __forceinline__ unsigned long long warp_xor_ull(unsigned long long v)
     for (int m = 16; m; m >>= 1) v ^= shfl_xor64(v, m);
     return v;
 }
+// Lexicographic (value, index) minimum over the warp for non-negative values and indices, on the warp-reduce unit
+// (three REDUX instead of five rounds of three shuffles): minimum of the high words, of the low words among the lanes
+// that hold it, of the indices among the lanes that hold both.
 __device__ __forceinline__ void warp_argmin(long long& s, int& i) {
-#pragma unroll
-    for (int m = 16; m; m >>= 1) {
-        const long long os = (long long)shfl_xor64((unsigned long long)s, m);
-        const int oi = __shfl_xor_sync(0xffffffffu, i, m);
-        if (os < s || (os == s && oi < i)) { s = os; i = oi; }
-    }
+    const unsigned hi = (unsigned)((unsigned long long)s >> 32), lo = (unsigned)s;
+    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+    const unsigned mi = __reduce_min_sync(0xffffffffu, (hi == mh && lo == ml) ? (unsigned)i : 0xffffffffu);
+    s = (long long)(((unsigned long long)mh << 32) | ml);
+    i = (int)mi;
+}
+// minimum of non-negative 64-bit values over the warp
+__device__ __forceinline__ long long warp_min_ll(long long s) {
+    const unsigned hi = (unsigned)((unsigned long long)s >> 32), lo = (unsigned)s;
+    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+    return (long long)(((unsigned long long)mh << 32) | ml);
+}
+// sum over the warp of values in [0, 2^60): three 20-bit digit sums on the warp-reduce unit
+__device__ __forceinline__ long long warp_sum_nonneg(long long v) {
+    const unsigned a = (unsigned)v & 0xfffffu, b = (unsigned)(v >> 20) & 0xfffffu, c = (unsigned)(v >> 40);
+    const unsigned long long A = __reduce_add_sync(0xffffffffu, a), B = __reduce_add_sync(0xffffffffu, b), C = __reduce_add_sync(0xffffffffu, c);
+    return (long long)(A + (B << 20) + (C << 40));
 }
 
 // exact integer reliability: q = rint(a * 2^(54-E)); a finite >= 0, E = frexp exponent of the frame max
