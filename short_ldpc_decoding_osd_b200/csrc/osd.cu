@@ -84,8 +84,7 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_kernel(OsdArgs a, const ui
                 int s_b = b32 + F.qd32[lane + 32] + wpop_shfl(tb, d0 ^ myprow[1]);
                 if (a.n_teps == 1) s_a = s_b = 0x7fffffff;  // order 0
                 int m = min(min(s_a, s_b), s_z);
-#pragma unroll
-                for (int x = 16; x; x >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, x));
+                m = __reduce_min_sync(0xffffffffu, m);
                 const int lim = m + OSD_WIN;
                 const bool cz = s_z <= lim;
                 unsigned ma = __ballot_sync(0xffffffffu, s_a <= lim), mb = __ballot_sync(0xffffffffu, s_b <= lim);
@@ -159,8 +158,7 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_kernel(OsdArgs a, const ui
                     }
                 }
                 int m = s0;
-#pragma unroll
-                for (int x = 16; x; x >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, x));
+                m = __reduce_min_sync(0xffffffffu, m);
                 if (lane == 0) S.red32[warp] = m;
                 __syncthreads();  // (B)
                 m = min(min(S.red32[0], S.red32[1]), min(S.red32[2], S.red32[3]));
@@ -384,8 +382,7 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_fs_kernel(OsdArgs a, FsParams
                         if (hd < fp.tau_psc && s < bs) { bs = s; bi = i; }
                     }
                     warp_argmin(bs, bi);
-#pragma unroll
-                    for (int m = 16; m; m >>= 1) first_stop = min(first_stop, __shfl_xor_sync(0xffffffffu, first_stop, m));
+                    first_stop = __reduce_min_sync(0xffffffffu, first_stop);
                     __syncthreads();  // previous use of the reduction slots is over
                     if (lane == 0) { S.red_s[w][warp] = bs; S.red_i[w][warp] = bi; S.red_stop[warp] = first_stop; }
                     __syncthreads();

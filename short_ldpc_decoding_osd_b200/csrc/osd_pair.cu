@@ -131,8 +131,7 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_pair_kernel(OsdArgs a, con
             }
             // ---- candidates inside the truncation window, exact scores ----------------------------------------------
             int m = s0;
-#pragma unroll
-            for (int x = 16; x; x >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, x));
+            m = __reduce_min_sync(0xffffffffu, m);
             const int lim = (((m >> 7) + OSD_WIN) << 7) | 127;
             unsigned cm = __ballot_sync(0xffffffffu, s0 <= lim);
             const int nc = __popc(cm);

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_pb_kernel(OsdArgs a, PbParams
 
         auto weighted = [&](unsigned long long D) -> long long {
             const long long s = (((D >> lane) & 1ull) ? q_l0 : 0ll) + (((D >> (lane + 32)) & 1ull) ? q_l1 : 0ll);
-            return warp_sum_nonneg(s);
+            return warp_sum_ll(s);
         };
         const unsigned long long d0 = P.d0;
         long long w_dmin = weighted(d0);

@@ -48,20 +48,16 @@ __device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int s
     unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
     return ((unsigned long long)hi << 32) | lo;
 }
-__device__ __forceinline__ unsigned long long shfl_xor64(unsigned long long v, int m) {
-    unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, m);
-    unsigned hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), m);
-    return ((unsigned long long)hi << 32) | lo;
-}
+// Warp reductions on the warp-reduce unit (REDUX: one instruction per 32-bit word instead of five shuffle rounds).
+// sum over the warp of values in [0, 2^60): three 20-bit digit sums
 __device__ __forceinline__ long long warp_sum_ll(long long v) {
-#pragma unroll
-    for (int m = 16; m; m >>= 1) v += (long long)shfl_xor64((unsigned long long)v, m);
-    return v;
+    const unsigned a = (unsigned)v & 0xfffffu, b = (unsigned)(v >> 20) & 0xfffffu, c = (unsigned)(v >> 40);
+    const unsigned long long A = __reduce_add_sync(0xffffffffu, a), B = __reduce_add_sync(0xffffffffu, b), C = __reduce_add_sync(0xffffffffu, c);
+    return (long long)(A + (B << 20) + (C << 40));
 }
 __device__ __forceinline__ unsigned long long warp_xor_ull(unsigned long long v) {
-#pragma unroll
-    for (int m = 16; m; m >>= 1) v ^= shfl_xor64(v, m);
-    return v;
+    const unsigned lo = __reduce_xor_sync(0xffffffffu, (unsigned)v), hi = __reduce_xor_sync(0xffffffffu, (unsigned)(v >> 32));
+    return ((unsigned long long)hi << 32) | lo;
 }
 // Lexicographic (value, index) minimum over the warp for non-negative values and indices, on the warp-reduce unit
 // (three REDUX instead of five rounds of three shuffles): minimum of the high words, of the low words among the lanes
@@ -80,12 +76,6 @@ __device__ __forceinline__ long long warp_min_ll(long long s) {
     const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
     const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
     return (long long)(((unsigned long long)mh << 32) | ml);
-}
-// sum over the warp of values in [0, 2^60): three 20-bit digit sums on the warp-reduce unit
-__device__ __forceinline__ long long warp_sum_nonneg(long long v) {
-    const unsigned a = (unsigned)v & 0xfffffu, b = (unsigned)(v >> 20) & 0xfffffu, c = (unsigned)(v >> 40);
-    const unsigned long long A = __reduce_add_sync(0xffffffffu, a), B = __reduce_add_sync(0xffffffffu, b), C = __reduce_add_sync(0xffffffffu, c);
-    return (long long)(A + (B << 20) + (C << 40));
 }
 
 // exact integer reliability: q = rint(a * 2^(54-E)); a finite >= 0, E = frexp exponent of the frame max
@@ -384,8 +374,7 @@ __device__ __forceinline__ Prep prepare_frame(const OsdArgs& a, FrameSm& F, cons
         as[k] = score_abs(ys[k]);
         amax_bits = max(amax_bits, __float_as_uint(as[k]));
     }
-#pragma unroll
-    for (int m = 16; m; m >>= 1) amax_bits = max(amax_bits, __shfl_xor_sync(0xffffffffu, amax_bits, m));
+    amax_bits = __reduce_max_sync(0xffffffffu, amax_bits);
     frexpf(__uint_as_float(amax_bits), &E);
     long long q[4];
 #pragma unroll
