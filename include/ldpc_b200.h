@@ -280,6 +280,18 @@ int ldpcb_dia_fir(ldpcb_t* h, const float* traj_dev, int64_t B, int n_rows, cons
                   float bias, float* out_dev, void* stream);
 
 /*
+ * NMS decode with the DIA reliability fused in: metric_dev[b,j] = bias + sum_{i=0..iters} taps_host[i] * posterior_i[b,j]
+ * (posterior_0 = the input LLR), accumulated in registers while the iterations run -- the same arithmetic as
+ * ldpcb_nms_decode(soft_traj) followed by ldpcb_dia_fir (one fused multiply-add per row in row order, bias last),
+ * without writing the (iters+1) x 128 trajectory to HBM.  Replaces Decoder_Layer.call (ms_test.py:99-101) followed by
+ * conv_bitwise.call (DL_OSD_Testing_serial/nn_net.py:190-197) on the frames handed to the DL OSD stage.  Always
+ * `iters` iterations (no early stop); taps_host holds iters+1 floats.
+ */
+int ldpcb_nms_decode_fir(ldpcb_t* h, const float* llr_dev, int64_t B, int iters, float alpha_check, float w_vc,
+                         float w_marg, const float* taps_host, float bias, uint32_t* hard_bits_dev,
+                         uint8_t* syndrome_nz_dev, float* metric_dev, void* stream);
+
+/*
  * DL sliding-window early termination over the block minima of ldpcb_osd_block_minima.  Replaces the window
  * bookkeeping of osd.sliding_osd (DL_OSD_Testing_serial/ordered_statistics_decoding.py:186-219) with
  * sliding_window_ops (:141-151) and the classifier Predict_outlier_light (nn_net.py:136-149: Dense(w+1, no

@@ -43,6 +43,7 @@ SYMBOLS = {
     "ldpcb_select_flagged": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "ldpcb_gather_rows": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "ldpcb_dia_fir": (_i32, [_vp, _vp, _i64, _i32, _vp, _f32, _vp, _vp]),
+    "ldpcb_nms_decode_fir": (_i32, [_vp, _vp, _i64, _i32, _f32, _f32, _f32, _vp, _f32, _vp, _vp, _vp, _vp]),
     "ldpcb_dl_window_policy": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ldpcb_tally": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp]),
     "ldpcb_decode": (_i32, [_vp, _vp, _i64, _i32, _f32, _f32, _f32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),

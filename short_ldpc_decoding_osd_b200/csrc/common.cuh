@@ -120,6 +120,11 @@ struct NmsArgs {
     uint8_t* iters_used;
     uint8_t* syndrome_nz;
     float* soft_traj;
+    // optional: DIA reliability fused into the decoder, fir_out[f,j] = fir_bias + sum_i fir_taps[i] * posterior_i[f,j]
+    // (posterior_0 = the input); excludes soft_traj and early_stop
+    float* fir_out = nullptr;
+    float fir_bias = 0.0f;
+    float fir_taps[LDPCB_MAX_ITERS + 1] = {};
 };
 int launch_nms(ldpcb_handle* h, const NmsArgs& a, cudaStream_t st);
 

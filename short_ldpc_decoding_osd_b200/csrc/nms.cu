@@ -28,7 +28,10 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
 }
 
 // REG8: every check has degree 8 (CCSDS): the edge labelled e of check c is stored at CV[e*96+rot[e]+c], no padding slots
-template <int DVA, int DVB, bool REG8, bool TRAJ, bool EARLY>
+// FIR: accumulate fir_taps[i] * posterior_i in registers while decoding (the DIA reliability of the DL scheme, aux.cu
+// dia_fir_kernel's arithmetic: one fused multiply-add per row in row order, bias added last) instead of writing the
+// 13-row trajectory to HBM and reading it back
+template <int DVA, int DVB, bool REG8, bool TRAJ, bool EARLY, bool FIR = false>
 __global__ void __launch_bounds__(NMS_THREADS, 3) nms_kernel(NmsArgs a, const NmsTables* __restrict__ tab) {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31;
@@ -107,6 +110,11 @@ __global__ void __launch_bounds__(NMS_THREADS, 3) nms_kernel(NmsArgs a, const Nm
         for (int k = 0; k < 4; ++k) hw[k] = __ballot_sync(0xffffffffu, !(y[k] > 0.0f));
         int it_used = 0;
         float soft[4] = {y[0], y[1], y[2], y[3]};
+        float fir[4] = {0.f, 0.f, 0.f, 0.f};
+        if (FIR) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) fir[k] = __fmaf_rn(a.fir_taps[0], y[k], 0.0f);
+        }
 
         for (int it = 0; it < a.iters; ++it) {
             // ---- check phase: vc = T - cv_old, min1/min2/sign, new cv ----
@@ -167,6 +175,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 3) nms_kernel(NmsArgs a, const Nm
                 soft[k] = __fadd_rn(S, __fmul_rn(a.w_marg, y[k]));
                 T[lane + 32 * k] = same_w ? soft[k] : __fadd_rn(S, __fmul_rn(a.w_vc, y[k]));
                 if (TRAJ) a.soft_traj[(f * rows + it + 1) * N + lane + 32 * k] = soft[k];
+                if (FIR) fir[k] = __fmaf_rn(a.fir_taps[it + 1], soft[k], fir[k]);
                 if (EARLY) hw[k] = __ballot_sync(0xffffffffu, !(soft[k] > 0.0f));
             }
             it_used = it + 1;
@@ -201,6 +210,10 @@ __global__ void __launch_bounds__(NMS_THREADS, 3) nms_kernel(NmsArgs a, const Nm
             const uint32_t w = lane == 0 ? hw[0] : lane == 1 ? hw[1] : lane == 2 ? hw[2] : hw[3];
             a.hard_bits[f * 4 + lane] = w;
         }
+        if (FIR) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a.fir_out[f * N + lane + 32 * k] = fir[k] + a.fir_bias;
+        }
         if (lane == 0) {
             if (a.iters_used) a.iters_used[f] = (uint8_t)it_used;
             if (a.syndrome_nz) a.syndrome_nz[f] = nz ? 1 : 0;
@@ -208,9 +221,9 @@ __global__ void __launch_bounds__(NMS_THREADS, 3) nms_kernel(NmsArgs a, const Nm
     }
 }
 
-template <int DVA, int DVB, bool REG8, bool TRAJ, bool EARLY>
+template <int DVA, int DVB, bool REG8, bool TRAJ, bool EARLY, bool FIR = false>
 static int launch_variant(ldpcb_handle* h, const NmsArgs& a, cudaStream_t st) {
-    auto kern = nms_kernel<DVA, DVB, REG8, TRAJ, EARLY>;
+    auto kern = nms_kernel<DVA, DVB, REG8, TRAJ, EARLY, FIR>;
     const int smem = NMS_WARPS * NMS_FRAME_FLOATS * (int)sizeof(float);
     static thread_local int occ_cache[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int& occ = occ_cache[h->device & 7];
@@ -230,6 +243,7 @@ static int launch_variant(ldpcb_handle* h, const NmsArgs& a, cudaStream_t st) {
 template <int DVA, int DVB, bool REG8>
 static int launch_deg(ldpcb_handle* h, const NmsArgs& a, cudaStream_t st) {
     const bool traj = a.soft_traj != nullptr, early = a.early_stop != 0;
+    if (a.fir_out) return launch_variant<DVA, DVB, REG8, false, false, true>(h, a, st);
     if (traj) return early ? launch_variant<DVA, DVB, REG8, true, true>(h, a, st) : launch_variant<DVA, DVB, REG8, true, false>(h, a, st);
     return early ? launch_variant<DVA, DVB, REG8, false, true>(h, a, st) : launch_variant<DVA, DVB, REG8, false, false>(h, a, st);
 }
@@ -260,5 +274,23 @@ extern "C" int ldpcb_nms_decode(ldpcb_t* h, const float* llr_dev, int64_t B, int
     a.alpha = alpha_check; a.w_vc = w_vc; a.w_marg = w_marg; a.early_stop = early_stop;
     a.hard_bits = hard_bits_dev; a.iters_used = iters_used_dev; a.syndrome_nz = syndrome_nz_dev;
     a.soft_traj = soft_traj_dev;
+    a.fir_out = nullptr;
+    return launch_nms(h, a, (cudaStream_t)stream);
+}
+
+extern "C" int ldpcb_nms_decode_fir(ldpcb_t* h, const float* llr_dev, int64_t B, int iters, float alpha_check, float w_vc,
+                                    float w_marg, const float* taps_host, float bias, uint32_t* hard_bits_dev,
+                                    uint8_t* syndrome_nz_dev, float* metric_dev, void* stream) {
+    if (!h) return LDPCB_ERR_ARG;
+    if (B < 0 || iters < 0 || iters > LDPCB_MAX_ITERS) return set_error(h, LDPCB_ERR_ARG, "ldpcb_nms_decode_fir: B=%lld iters=%d out of range", (long long)B, iters);
+    if (B == 0) return LDPCB_OK;
+    if (!llr_dev || !hard_bits_dev || !taps_host || !metric_dev) return set_error(h, LDPCB_ERR_ARG, "ldpcb_nms_decode_fir: NULL llr, hard_bits, taps or metric");
+    if (((uintptr_t)llr_dev & 15) != 0) return set_error(h, LDPCB_ERR_ALIGN, "ldpcb_nms_decode_fir: llr must be 16-byte aligned");
+    NmsArgs a;
+    a.llr = llr_dev; a.idx = nullptr; a.B = B; a.iters = iters;
+    a.alpha = alpha_check; a.w_vc = w_vc; a.w_marg = w_marg; a.early_stop = 0;
+    a.hard_bits = hard_bits_dev; a.iters_used = nullptr; a.syndrome_nz = syndrome_nz_dev; a.soft_traj = nullptr;
+    a.fir_out = metric_dev; a.fir_bias = bias;
+    for (int i = 0; i <= LDPCB_MAX_ITERS; ++i) a.fir_taps[i] = i <= iters ? taps_host[i] : 0.0f;
     return launch_nms(h, a, (cudaStream_t)stream);
 }

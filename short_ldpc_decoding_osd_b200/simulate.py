@@ -184,10 +184,9 @@ def run_point_dl(handle, ebn0_db: float, total_frames: int, tep_info, taps, bias
                 llr_f, truth_f = e((nf, 128), torch.float32), e((nf, 4), torch.int32)
                 handle.call("ldpcb_gather_rows", llr, idx, cnt, nf, 128, llr_f, stream)
                 handle.call("ldpcb_gather_rows", truth.view(torch.float32), idx, cnt, nf, 4, truth_f.view(torch.float32), stream)
-                traj, bits_f = e((nf, rows, 128), torch.float32), e((nf, 4), torch.int32)
-                handle.call("ldpcb_nms_decode", llr_f, nf, iters, float(alpha), 1.0, 1.0, 0, bits_f, None, None, traj, stream)
-                metric = e((nf, 128), torch.float32)
-                handle.call("ldpcb_dia_fir", traj, nf, rows, taps, float(bias), metric, stream)
+                bits_f, metric = e((nf, 4), torch.int32), e((nf, 128), torch.float32)
+                # second NMS pass over the failures with the DIA FIR fused in: the 13-row trajectories never reach HBM
+                handle.call("ldpcb_nms_decode_fir", llr_f, nf, iters, float(alpha), 1.0, 1.0, taps, float(bias), bits_f, None, metric, stream)
                 bm, ex, ts = e((nf, nb), torch.int64), e((nf,), torch.int32), e((nf,), torch.int64)
                 handle.call("ldpcb_osd_block_minima", metric, llr_f, nf, packed, int(packed.numel()), starts, nb, FLAGS_DL, bm, None, ex,
                             truth_f, ts, None, stream)

@@ -129,6 +129,31 @@ def test_dia_fir(handle):
     np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
 
 
+
+def test_nms_decode_fir_equals_trajectory_then_fir(handle, code):
+    """ldpcb_nms_decode_fir (DIA FIR fused into the decoder) is bit-identical to ldpcb_nms_decode(soft_traj) followed by
+    ldpcb_dia_fir, and its hard decisions / syndrome flags equal the plain decode."""
+    B = 3001
+    y = empty((B, 128), torch.float32)
+    tr = empty((B, 4), torch.int32)
+    handle.call("ldpcb_gen_frames", 55, 0, B, 2.0, y, tr, None)
+    rng = np.random.default_rng(8)
+    taps = (np.full(13, 1 / 13) + 0.05 * rng.normal(size=13)).astype(np.float32)
+    bits = empty((B, 4), torch.int32)
+    syn = empty((B,), torch.uint8)
+    traj = empty((B, 13, 128), torch.float32)
+    handle.call("ldpcb_nms_decode", y, B, 12, ALPHA, 1.0, 1.0, 0, bits, None, syn, traj, None)
+    want = empty((B, 128), torch.float32)
+    handle.call("ldpcb_dia_fir", traj, B, 13, taps, 0.07, want, None)
+    bits2 = empty((B, 4), torch.int32)
+    syn2 = empty((B,), torch.uint8)
+    got = empty((B, 128), torch.float32)
+    handle.call("ldpcb_nms_decode_fir", y, B, 12, ALPHA, 1.0, 1.0, taps, 0.07, bits2, syn2, got, None)
+    sync()
+    assert torch.equal(got, want)
+    assert torch.equal(bits, bits2) and torch.equal(syn, syn2)
+
+
 def test_host_entry_points_equal_device_ones(handle, code):
     B = 70000  # more than one host chunk
     y, cw, _ = PO.gen_frames(8, 0, B, 2.5, code.G)
