@@ -139,9 +139,9 @@ def run_point(handle, ebn0_db: float, total_frames: int, seed: int = 0, osd_orde
 def run_point_dl(handle, ebn0_db: float, total_frames: int, tep_info, taps, bias: float, W1, W2, soft_margin: float = 0.9,
                  win_width: int = 5, seed: int = 0, iters: int = 12, alpha: float = 0.66943514, chunk: int = 1 << 20,
                  rank: int = 0, world: int = 1):
-    """One Eb/N0 point of the DL scheme (BASELINE config 4), everything on the device: generate -> NMS -> detected
-    failures re-decoded with their 13-row trajectories -> DIA FIR (ordering metric) -> block minima along the
-    decoding path, scored against the channel LLR -> sliding-window policy.  Mirrors Ldpc_128_testing followed by
+    """One Eb/N0 point of the DL scheme (BASELINE config 4), everything on the device: generate -> NMS with the DIA FIR
+    (ordering metric) fused in -> detected failures -> block minima along the decoding path, scored against the
+    channel LLR -> sliding-window policy.  Mirrors Ldpc_128_testing followed by
     DL_OSD_Testing_serial/nn_testing.Testing_OSD (:159-256).  tep_info = (list of int[T_b,64] blocks over DL MRB
     indices, cumulative sizes) as nn_testing.generate_teps returns.  -> (Tallies of the NMS stage, dict of DL sums)."""
     import torch
@@ -176,17 +176,19 @@ def run_point_dl(handle, ebn0_db: float, total_frames: int, tep_info, taps, bias
             its, syn = e((m,), torch.uint8), e((m,), torch.uint8)
             idx, cnt = e((m,), torch.int32), e((1,), torch.int32)
             handle.call("ldpcb_gen_frames", int(seed), int(done + a), m, float(ebn0_db), llr, truth, stream)
-            handle.call("ldpcb_nms_decode", llr, m, iters, float(alpha), 1.0, 1.0, 0, bits, its, syn, None, stream)
+            # one NMS pass with the DIA FIR fused in: the ordering metric of every frame costs four multiply-adds per
+            # iteration and 512 B of HBM, far less than re-decoding the detected failures for their trajectories
+            metric_all = e((m, 128), torch.float32)
+            its.fill_(iters)
+            handle.call("ldpcb_nms_decode_fir", llr, m, iters, float(alpha), 1.0, 1.0, taps, float(bias), bits, syn, metric_all, stream)
             handle.call("ldpcb_tally", bits, syn, its, None, None, -1, 0, truth, m, counters, stream)
             handle.call("ldpcb_select_flagged", syn, m, idx, cnt, stream)
             nf = int(cnt.item())
             if nf > 0:
-                llr_f, truth_f = e((nf, 128), torch.float32), e((nf, 4), torch.int32)
+                llr_f, truth_f, metric = e((nf, 128), torch.float32), e((nf, 4), torch.int32), e((nf, 128), torch.float32)
                 handle.call("ldpcb_gather_rows", llr, idx, cnt, nf, 128, llr_f, stream)
+                handle.call("ldpcb_gather_rows", metric_all, idx, cnt, nf, 128, metric, stream)
                 handle.call("ldpcb_gather_rows", truth.view(torch.float32), idx, cnt, nf, 4, truth_f.view(torch.float32), stream)
-                bits_f, metric = e((nf, 4), torch.int32), e((nf, 128), torch.float32)
-                # second NMS pass over the failures with the DIA FIR fused in: the 13-row trajectories never reach HBM
-                handle.call("ldpcb_nms_decode_fir", llr_f, nf, iters, float(alpha), 1.0, 1.0, taps, float(bias), bits_f, None, metric, stream)
                 bm, ex, ts = e((nf, nb), torch.int64), e((nf,), torch.int32), e((nf,), torch.int64)
                 handle.call("ldpcb_osd_block_minima", metric, llr_f, nf, packed, int(packed.numel()), starts, nb, FLAGS_DL, bm, None, ex,
                             truth_f, ts, None, stream)
