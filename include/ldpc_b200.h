@@ -14,10 +14,15 @@
  *  - Every call returns LDPCB_OK (0) or a negative ldpcb_status; nothing throws across the ABI.
  *    ldpcb_last_error() returns a human-readable message for the last failure on that handle.
  *  - Device-pointer calls are asynchronous on `stream` (a cudaStream_t passed as void*, NULL =
- *    default stream) and never synchronise.  *_host calls are synchronous: they return when
- *    the results are in the host buffers.
+ *    default stream).  They do not synchronise, with one exception: calls that need scratch memory
+ *    (ldpcb_decode, ldpcb_simulate, ldpcb_select_flagged, ldpcb_osd_pb_decode) keep one scratch buffer per
+ *    caller stream; its first use allocates and a later call with a larger batch re-allocates after a
+ *    cudaDeviceSynchronize.  Warm a stream up with the largest batch to keep the steady state asynchronous.
+ *    *_host calls are synchronous: they return when the results are in the host buffers.
  *  - One handle per (process, device).  A handle is not thread-safe; different handles are
- *    independent.
+ *    independent, also on different devices in one thread: every entry point makes the handle's
+ *    device current for the duration of the call and restores the caller's device on return
+ *    (ldpcb_create included).  Calls of ONE handle on different streams may overlap on the device.
  *  - LLR rows are 128 contiguous floats and must be 16-byte aligned (128-bit loads).
  *  - Bit packing is little-endian: bit j of a frame is (w[j >> 5] >> (j & 31)) & 1, with
  *    uint32_t w[4] per frame.  Bit value 1 means "LLR <= 0" (reference: tf.where(x>0,0,1),
@@ -359,6 +364,10 @@ int ldpcb_decode_host(ldpcb_t* h, const float* llr_host, int64_t B, int iters, f
                       float w_marg, int early_stop, int osd_order, int tep_order,
                       uint32_t* final_bits_host, uint8_t* syndrome_nz_host, int32_t* best_tep_host,
                       const uint32_t* truth_bits_host, uint64_t* counters_host);
+
+/* PCI bus id ("0000:1b:00.0") of a CUDA device, for callers that bind their host threads and pinned buffers to the
+ * GPU's NUMA node (/sys/bus/pci/devices/<id>/numa_node) before ldpcb_host_alloc's first touch.  len >= 13. */
+int ldpcb_device_pci_bus_id(int device, char* buf, int len);
 
 /* Pinned host memory for the *_host calls. */
 int ldpcb_host_alloc(void** p, uint64_t bytes);

@@ -56,6 +56,7 @@ SYMBOLS = {
     "ldpcb_osd_pb_decode": (_i32, [_vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
     "ldpcb_osd_pb_decode_host": (_i32, [_vp, _vp, _i64, _i32, _f32, _vp, _vp]),
     "ldpcb_decode_host": (_i32, [_vp, _vp, _i64, _i32, _f32, _f32, _f32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "ldpcb_device_pci_bus_id": (_i32, [_i32, C.c_char_p, _i32]),
     "ldpcb_host_alloc": (_i32, [C.POINTER(_vp), _u64]),
     "ldpcb_host_free": (_i32, [_vp]),
     "ldpcb_launch_count": (_u64, [_vp]),
@@ -169,31 +170,74 @@ class Handle:
         return out
 
 
-def pinned_empty(shape, dtype) -> np.ndarray:
-    """NumPy array backed by pinned host memory (ldpcb_host_alloc); freed when collected."""
-    lib = load()
+class _PinnedBlock:
+    """Owner of one cudaMallocHost block.  Every array handed out is a view whose ultimate ``.base`` is the
+    ndarray built from this object's ``__array_interface__``, and that ndarray keeps this object alive -- so the
+    block is freed only when the last view (slice, reshape, .view()) of it is gone."""
+
+    def __init__(self, lib, nbytes: int):
+        p = _vp()
+        st = lib.ldpcb_host_alloc(C.byref(p), max(nbytes, 1))
+        if st != 0:
+            raise LdpcB200Error(st, lib.ldpcb_last_error(None).decode())
+        self._lib, self.ptr, self.nbytes = lib, p.value, nbytes
+        self.__array_interface__ = {"data": (self.ptr, False), "shape": (max(nbytes, 1),), "typestr": "|u1", "version": 3}
+
+    def __del__(self):
+        ptr, self.ptr = getattr(self, "ptr", None), None
+        if ptr:
+            try:
+                self._lib.ldpcb_host_free(ptr)
+            except Exception:
+                pass
+
+
+def pinned_empty(shape, dtype, _alloc=None) -> np.ndarray:
+    """NumPy array backed by pinned host memory (ldpcb_host_alloc); the memory is released when the array AND
+    every view derived from it have been collected.  `_alloc` (tests) substitutes the block allocator."""
     dt = np.dtype(dtype)
-    nbytes = int(np.prod(shape)) * dt.itemsize
-    p = _vp()
-    st = lib.ldpcb_host_alloc(C.byref(p), max(nbytes, 1))
-    if st != 0:
-        raise LdpcB200Error(st, lib.ldpcb_last_error(None).decode())
-    buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
-    _PINNED[id(buf)] = (buf, p.value)
-    import weakref
-
-    weakref.finalize(arr, _free_pinned, id(buf))
-    return arr
+    count = int(np.prod(shape))
+    nbytes = count * dt.itemsize
+    block = (_alloc or (lambda n: _PinnedBlock(load(), n)))(nbytes)
+    raw = np.asarray(block)  # base -> block
+    return raw[:nbytes].view(dt).reshape(shape)
 
 
-_PINNED = {}
+def device_numa_node(device: int) -> int:
+    """NUMA node of a CUDA device from sysfs, -1 if unknown (single-node hosts report -1 or 0)."""
+    buf = C.create_string_buffer(32)
+    if load().ldpcb_device_pci_bus_id(int(device), buf, 32) != 0:
+        return -1
+    try:
+        with open(f"/sys/bus/pci/devices/{buf.value.decode().lower()}/numa_node") as f:
+            return int(f.read().strip())
+    except (OSError, ValueError):
+        return -1
 
 
-def _free_pinned(key) -> None:
-    ent = _PINNED.pop(key, None)
-    if ent is not None and _LIB is not None:
-        _LIB.ldpcb_host_free(ent[1])
+def bind_host_to_device(device: int) -> dict:
+    """Restrict this process to the CPUs of the NUMA node `device` hangs off, so that pinned buffers allocated (and
+    first touched) afterwards live in the memory closest to the GPU's PCIe root port.  A no-op on hosts with one
+    node.  Returns what was done (bench.py prints it)."""
+    node = device_numa_node(device)
+    info = {"numa_node": node, "bound": False}
+    try:
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        info["numa_nodes"] = len(nodes)
+        if node < 0 or len(nodes) <= 1:
+            return info
+        cpus = set()
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update(bound=True, cpus=len(cpus))
+    except (OSError, ValueError, AttributeError) as e:
+        info["error"] = str(e)[:100]
+    return info
 
 
 def unpack_bits(words: np.ndarray) -> np.ndarray:

@@ -334,7 +334,7 @@ extern "C" int ldpcb_tally(ldpcb_t* h, const uint32_t* nms_bits_dev, const uint8
                            const uint8_t* iters_used_dev, const uint32_t* final_bits_dev, const int32_t* best_tep_dev,
                            int osd_order, int tep_order, const uint32_t* truth_bits_dev, int64_t B,
                            uint64_t* counters_dev, void* stream) {
-    if (!h) return LDPCB_ERR_ARG;
+    LDPCB_ENTER(h);
     if (B < 0 || !truth_bits_dev || !counters_dev || (!nms_bits_dev && !final_bits_dev))
         return set_error(h, LDPCB_ERR_ARG, "ldpcb_tally: bad arguments");
     if (final_bits_dev && (osd_order < -1 || osd_order > 3 || tep_order < 0 || tep_order > 1))
@@ -348,17 +348,18 @@ extern "C" int ldpcb_tally(ldpcb_t* h, const uint32_t* nms_bits_dev, const uint8
 
 extern "C" int ldpcb_select_flagged(ldpcb_t* h, const uint8_t* flags_dev, int64_t B, int32_t* idx_dev,
                                     int32_t* count_dev, void* stream) {
-    if (!h) return LDPCB_ERR_ARG;
+    LDPCB_ENTER(h);
     if (B < 0 || B > 0x7fffffff || !count_dev || (B > 0 && (!flags_dev || !idx_dev)))
         return set_error(h, LDPCB_ERR_ARG, "ldpcb_select_flagged: bad arguments");
-    int st = ensure_ws(h, 0, select_temp_bytes(B));
+    char* temp = nullptr;
+    int st = ensure_stream_ws(h, (cudaStream_t)stream, select_temp_bytes(B), &temp);
     if (st != LDPCB_OK) return st;
-    return launch_select(h, flags_dev, B, idx_dev, count_dev, h->ws[0].buf, (cudaStream_t)stream);
+    return launch_select(h, flags_dev, B, idx_dev, count_dev, temp, (cudaStream_t)stream);
 }
 
 extern "C" int ldpcb_gather_rows(ldpcb_t* h, const float* src_dev, const int32_t* idx_dev, const int32_t* count_dev,
                                  int64_t max_rows, int row_floats, float* dst_dev, void* stream) {
-    if (!h) return LDPCB_ERR_ARG;
+    LDPCB_ENTER(h);
     if (max_rows < 0 || row_floats <= 0 || (row_floats & 3) || !src_dev || !idx_dev || !dst_dev)
         return set_error(h, LDPCB_ERR_ARG, "ldpcb_gather_rows: bad arguments");
     if ((((uintptr_t)src_dev) | ((uintptr_t)dst_dev)) & 15) return set_error(h, LDPCB_ERR_ALIGN, "ldpcb_gather_rows: 16-byte alignment required");
@@ -373,7 +374,7 @@ extern "C" int ldpcb_gather_rows(ldpcb_t* h, const float* src_dev, const int32_t
 
 extern "C" int ldpcb_dia_fir(ldpcb_t* h, const float* traj_dev, int64_t B, int n_rows, const float* taps_host,
                              float bias, float* out_dev, void* stream) {
-    if (!h) return LDPCB_ERR_ARG;
+    LDPCB_ENTER(h);
     if (B < 0 || n_rows < 1 || n_rows > FIR_MAX_ROWS || !traj_dev || !taps_host || !out_dev)
         return set_error(h, LDPCB_ERR_ARG, "ldpcb_dia_fir: bad arguments");
     if ((((uintptr_t)traj_dev) | ((uintptr_t)out_dev)) & 15) return set_error(h, LDPCB_ERR_ALIGN, "ldpcb_dia_fir: 16-byte alignment required");
@@ -392,7 +393,7 @@ extern "C" int ldpcb_dl_window_policy(ldpcb_t* h, const int64_t* block_min_q_dev
                                       const float* W1_host, const float* W2_host, float soft_margin,
                                       const int32_t* acc_block_size_host, uint8_t* success_dev, int32_t* windows_dev,
                                       int32_t* complexity_dev, uint64_t* counters_dev, void* stream) {
-    if (!h) return LDPCB_ERR_ARG;
+    LDPCB_ENTER(h);
     if (B < 0 || win_width < 1 || win_width > DLW_MAX_WIDTH || n_blocks < win_width || n_blocks > DLW_MAX_BLOCKS)
         return set_error(h, LDPCB_ERR_ARG, "ldpcb_dl_window_policy: B=%lld n_blocks=%d win_width=%d out of range", (long long)B, n_blocks, win_width);
     if (!block_min_q_dev || !score_exp_dev || !W1_host || !W2_host || !acc_block_size_host)

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -65,6 +66,9 @@ struct Workspace {
     char* buf = nullptr;
     size_t cap = 0;
 };
+// slots of ldpcb_handle::occ (occupancy is a property of (kernel, device), so it lives in the handle)
+enum { OCC_NMS = 0 /* +0..7: template variants */, OCC_NMS_QC = 8 /* +0..3 */, OCC_OSD = 12 /* +0..9 */, OCC_OSD_FS = 22, OCC_OSD_PAIR = 23,
+       OCC_OSD_PB = 24, OCC_OSD3 = 25, OCC_SIM = 26 /* +0..1 */, OCC_SLOTS = 32 };
 
 }  // namespace ldpcb
 
@@ -80,7 +84,10 @@ struct ldpcb_handle {
     uint64_t gcol_host[ldpcb::N];
     ldpcb::TepTable tep[4][2];      // [order][tep_order]
     int32_t* one_block_dev = nullptr;  // {0, n} scratch for single-block calls
-    ldpcb::Workspace ws[ldpcb::NUM_WS];
+    ldpcb::Workspace ws[ldpcb::NUM_WS];   // [1..3]: the *_host pipelines' private slots, [0]: their shared counters
+    std::map<cudaStream_t, ldpcb::Workspace> stream_ws;  // scratch of the device-pointer calls, one per caller stream
+    int occ[ldpcb::OCC_SLOTS] = {};       // resident CTAs per SM of each kernel variant on THIS handle's device (0 = not queried)
+    bool pb_consts_ready = false;         // __constant__ tables of osd_pb.cu uploaded to this device
     char* pb_list = nullptr;       // PB-OSD order 3: TEP lists of the resident warps
     size_t pb_list_cap = 0;        // in list entries
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
@@ -94,6 +101,27 @@ int set_error(ldpcb_handle* h, int code, const char* fmt, ...);
 int check_cuda(ldpcb_handle* h, cudaError_t e, const char* what);
 // Grow workspace slot `slot` to at least `bytes` (cudaMalloc on growth only).
 int ensure_ws(ldpcb_handle* h, int slot, size_t bytes);
+// Scratch of a device-pointer call, private to the caller's stream (two calls on different streams never share it).
+// First use on a stream and growth allocate, and growth synchronises the device (documented in ldpc_b200.h).
+int ensure_stream_ws(ldpcb_handle* h, cudaStream_t st, size_t bytes, char** buf);
+
+// Makes the handle's device current for the duration of an entry point and restores the caller's device on return,
+// so handles of several devices can be used from one thread.
+struct DeviceGuard {
+    int prev = -1, want = -1;
+    explicit DeviceGuard(const ldpcb_handle* h) {
+        if (!h) return;
+        want = h->device;
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        if (prev != want) cudaSetDevice(want);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0 && prev != want) cudaSetDevice(prev);
+    }
+};
+#define LDPCB_ENTER(h)                   \
+    if (!(h)) return LDPCB_ERR_ARG;      \
+    ldpcb::DeviceGuard _ldpcb_guard(h)
 
 #define LDPCB_CUDA(h, call)                                         \
     do {                                                            \

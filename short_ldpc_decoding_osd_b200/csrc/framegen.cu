@@ -102,7 +102,7 @@ using namespace ldpcb;
 
 extern "C" int ldpcb_gen_frames(ldpcb_t* h, uint64_t seed, uint64_t first_frame, int64_t B, float ebn0_db,
                                 float* llr_dev, uint32_t* cw_bits_dev, void* stream) {
-    if (!h) return LDPCB_ERR_ARG;
+    LDPCB_ENTER(h);
     if (B < 0 || (!llr_dev && !cw_bits_dev)) return set_error(h, LDPCB_ERR_ARG, "ldpcb_gen_frames: bad arguments");
     if (llr_dev && ((uintptr_t)llr_dev & 15)) return set_error(h, LDPCB_ERR_ALIGN, "ldpcb_gen_frames: llr must be 16-byte aligned");
     return launch_gen(h, seed, first_frame, B, ebn0_db, llr_dev, cw_bits_dev, (cudaStream_t)stream);

@@ -27,8 +27,10 @@ int check_cuda(ldpcb_handle* h, cudaError_t e, const char* what) {
     return set_error(h, LDPCB_ERR_CUDA, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
 }
 
-int ensure_ws(ldpcb_handle* h, int slot, size_t bytes) {
-    Workspace& w = h->ws[slot];
+static int grow(ldpcb_handle* h, Workspace& w, size_t bytes);
+int ensure_ws(ldpcb_handle* h, int slot, size_t bytes) { return grow(h, h->ws[slot], bytes); }
+
+static int grow(ldpcb_handle* h, Workspace& w, size_t bytes) {
     if (w.cap >= bytes) return LDPCB_OK;
     if (w.buf) {
         // the buffer may still be in use by queued work of this handle
@@ -41,6 +43,13 @@ int ensure_ws(ldpcb_handle* h, int slot, size_t bytes) {
     LDPCB_CUDA(h, cudaMalloc(&w.buf, cap));
     w.cap = cap;
     return LDPCB_OK;
+}
+
+int ensure_stream_ws(ldpcb_handle* h, cudaStream_t st, size_t bytes, char** buf) {
+    Workspace& w = h->stream_ws[st];
+    int s = grow(h, w, bytes);
+    *buf = w.buf;
+    return s;
 }
 
 // ---- TEP enumerations -------------------------------------------------------------------------
@@ -344,6 +353,7 @@ int ldpcb_create(ldpcb_t** out, const uint8_t* H_host, const uint8_t* G_host, in
     ldpcb_handle* h = new ldpcb_handle();
     h->device = device;
     int st = LDPCB_OK;
+    DeviceGuard guard(h);  // the caller's current device is restored when ldpcb_create returns
     auto fail = [&](int code) {
         g_create_error = h->err;
         ldpcb_destroy(h);
@@ -372,7 +382,7 @@ int ldpcb_create(ldpcb_t** out, const uint8_t* H_host, const uint8_t* G_host, in
 
 void ldpcb_destroy(ldpcb_t* h) {
     if (!h) return;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h);
     cudaDeviceSynchronize();
     for (int o = 0; o < 4; ++o)
         for (int kd = 0; kd < 2; ++kd) {
@@ -381,6 +391,8 @@ void ldpcb_destroy(ldpcb_t* h) {
         }
     for (int i = 0; i < NUM_WS; ++i)
         if (h->ws[i].buf) cudaFree(h->ws[i].buf);
+    for (auto& kv : h->stream_ws)
+        if (kv.second.buf) cudaFree(kv.second.buf);
     if (h->pb_list) cudaFree(h->pb_list);
     for (int i = 0; i < 3; ++i) {
         if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
@@ -411,6 +423,13 @@ int ldpcb_tep_table(ldpcb_t* h, int order, int tep_order, uint32_t* teps_host) {
     if (n < 0) return n;
     if (!teps_host) return set_error(h, LDPCB_ERR_ARG, "ldpcb_tep_table: NULL output");
     memcpy(teps_host, h->tep[order][tep_order].host.data(), sizeof(uint32_t) * n);
+    return LDPCB_OK;
+}
+
+int ldpcb_device_pci_bus_id(int device, char* buf, int len) {
+    if (!buf || len < 13) return LDPCB_ERR_ARG;
+    cudaError_t e = cudaDeviceGetPCIBusId(buf, len, device);
+    if (e != cudaSuccess) { cudaGetLastError(); buf[0] = 0; return set_error(nullptr, LDPCB_ERR_CUDA, "cudaDeviceGetPCIBusId(%d): %s", device, cudaGetErrorString(e)); }
     return LDPCB_OK;
 }
 

@@ -225,8 +225,7 @@ template <int DVA, int DVB, bool REG8, bool TRAJ, bool EARLY, bool FIR = false>
 static int launch_variant(ldpcb_handle* h, const NmsArgs& a, cudaStream_t st) {
     auto kern = nms_kernel<DVA, DVB, REG8, TRAJ, EARLY, FIR>;
     const int smem = NMS_WARPS * NMS_FRAME_FLOATS * (int)sizeof(float);
-    static thread_local int occ_cache[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int& occ = occ_cache[h->device & 7];
+    int& occ = h->occ[OCC_NMS + (TRAJ ? 1 : 0) + (EARLY ? 2 : 0) + (FIR ? 4 : 0)];
     if (occ == 0) {
         LDPCB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NMS_THREADS, smem));
         if (occ < 1) occ = 1;
@@ -264,7 +263,7 @@ extern "C" int ldpcb_nms_decode(ldpcb_t* h, const float* llr_dev, int64_t B, int
                                 float w_vc, float w_marg, int early_stop, uint32_t* hard_bits_dev,
                                 uint8_t* iters_used_dev, uint8_t* syndrome_nz_dev, float* soft_traj_dev,
                                 void* stream) {
-    if (!h) return LDPCB_ERR_ARG;
+    LDPCB_ENTER(h);
     if (B < 0 || iters < 0 || iters > LDPCB_MAX_ITERS) return set_error(h, LDPCB_ERR_ARG, "ldpcb_nms_decode: B=%lld iters=%d out of range", (long long)B, iters);
     if (B == 0) return LDPCB_OK;
     if (!llr_dev || !hard_bits_dev) return set_error(h, LDPCB_ERR_ARG, "ldpcb_nms_decode: NULL llr or hard_bits");
@@ -281,7 +280,7 @@ extern "C" int ldpcb_nms_decode(ldpcb_t* h, const float* llr_dev, int64_t B, int
 extern "C" int ldpcb_nms_decode_fir(ldpcb_t* h, const float* llr_dev, int64_t B, int iters, float alpha_check, float w_vc,
                                     float w_marg, const float* taps_host, float bias, uint32_t* hard_bits_dev,
                                     uint8_t* syndrome_nz_dev, float* metric_dev, void* stream) {
-    if (!h) return LDPCB_ERR_ARG;
+    LDPCB_ENTER(h);
     if (B < 0 || iters < 0 || iters > LDPCB_MAX_ITERS) return set_error(h, LDPCB_ERR_ARG, "ldpcb_nms_decode_fir: B=%lld iters=%d out of range", (long long)B, iters);
     if (B == 0) return LDPCB_OK;
     if (!llr_dev || !hard_bits_dev || !taps_host || !metric_dev) return set_error(h, LDPCB_ERR_ARG, "ldpcb_nms_decode_fir: NULL llr, hard_bits, taps or metric");

@@ -471,8 +471,7 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_fs_kernel(OsdArgs a, FsParams
 int launch_osd_fs(ldpcb_handle* h, const OsdArgs& a, const FsParams& fp, cudaStream_t st) {
     if (a.B == 0) return LDPCB_OK;
     const int smem = (int)sizeof(OsdSmem);
-    static thread_local int occ_cache[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int& occ = occ_cache[h->device & 7];
+    int& occ = h->occ[OCC_OSD_FS];
     if (occ == 0) {
         LDPCB_CUDA(h, cudaFuncSetAttribute(osd_fs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         LDPCB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, osd_fs_kernel, OSD_THREADS, smem));
@@ -491,8 +490,7 @@ template <int MAXW, bool BLOCKS, bool SOLO = false>
 static int launch_variant(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st) {
     auto kern = osd_kernel<MAXW, BLOCKS, SOLO>;
     const int smem = SOLO ? OSD_FPB * (int)sizeof(FrameSm) : (int)sizeof(OsdSmem);
-    static thread_local int occ_cache[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int& occ = occ_cache[h->device & 7];
+    int& occ = h->occ[OCC_OSD + (SOLO ? 8 : (MAXW - 1) * 2 + (BLOCKS ? 1 : 0))];
     if (occ == 0) {
         LDPCB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         LDPCB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, OSD_THREADS, smem));
@@ -537,7 +535,7 @@ extern "C" int ldpcb_osd_decode(ldpcb_t* h, const float* order_llr_dev, const fl
                                 int order, int tep_order, int flags, uint32_t* cw_bits_dev, int32_t* best_tep_dev,
                                 int64_t* best_score_q_dev, int32_t* score_exp_dev, uint8_t* perm_dev,
                                 uint64_t* redG_dev, void* stream) {
-    if (!h) return LDPCB_ERR_ARG;
+    LDPCB_ENTER(h);
     if (B < 0 || order < 0 || order > 3 || tep_order < 0 || tep_order > 1 || (flags & ~3))
         return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_decode: B=%lld order=%d tep_order=%d flags=%d out of range", (long long)B, order, tep_order, flags);
     if (B == 0) return LDPCB_OK;
@@ -558,7 +556,7 @@ extern "C" int ldpcb_osd_block_minima(ldpcb_t* h, const float* order_llr_dev, co
                                       int32_t n_blocks, int flags, int64_t* block_min_q_dev, int32_t* block_arg_dev,
                                       int32_t* score_exp_dev, const uint32_t* truth_bits_dev,
                                       int64_t* truth_score_q_dev, uint8_t* perm_dev, void* stream) {
-    if (!h) return LDPCB_ERR_ARG;
+    LDPCB_ENTER(h);
     if (B < 0 || n_teps < 0 || n_blocks < 1 || (flags & ~3))
         return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_block_minima: B=%lld n_teps=%d n_blocks=%d flags=%d out of range", (long long)B, n_teps, n_blocks, flags);
     if (B == 0) return LDPCB_OK;
@@ -579,7 +577,7 @@ extern "C" int ldpcb_osd_fs_decode(ldpcb_t* h, const float* llr_dev, int64_t B, 
                                    float beta_shift, uint32_t* cw_bits_dev, int32_t* best_tep_dev, int32_t* num_teps_dev,
                                    uint8_t* stop_kind_dev, int64_t* best_score_q_dev, int32_t* score_exp_dev,
                                    uint8_t* perm_dev, void* stream) {
-    if (!h) return LDPCB_ERR_ARG;
+    LDPCB_ENTER(h);
     if (B < 0 || order_limit < 0 || order_limit > 3)
         return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_fs_decode: B=%lld order_limit=%d out of range", (long long)B, order_limit);
     if (B == 0) return LDPCB_OK;

@@ -247,8 +247,7 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_pair_kernel(OsdArgs a, con
 int launch_osd_pair(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st) {
     if (a.B == 0) return LDPCB_OK;
     const int smem = (int)sizeof(PairSmem);
-    static thread_local int occ_cache[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int& occ = occ_cache[h->device & 7];
+    int& occ = h->occ[OCC_OSD_PAIR];
     if (occ == 0) {
         LDPCB_CUDA(h, cudaFuncSetAttribute(osd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         LDPCB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, osd_pair_kernel, OSD_THREADS, smem));

@@ -261,8 +261,7 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_pb_kernel(OsdArgs a, PbParams
 
 int launch_osd_pb(ldpcb_handle* h, const OsdArgs& a, const PbParams& pp, cudaStream_t st) {
     if (a.B == 0) return LDPCB_OK;
-    static bool consts_ready[8] = {false, false, false, false, false, false, false, false};
-    if (!consts_ready[h->device & 7]) {
+    if (!h->pb_consts_ready) {
         double c[65];
         unsigned __int128 e = 1;  // exact integers, rounded once to fp64 like Python's float(math.comb(64, i))
         c[0] = 1.0;
@@ -271,13 +270,12 @@ int launch_osd_pb(ldpcb_handle* h, const OsdArgs& a, const PbParams& pp, cudaStr
             c[i] = (double)(unsigned long long)e;
         }
         LDPCB_CUDA(h, cudaMemcpyToSymbol(c_binom64, c, sizeof c));
-        consts_ready[h->device & 7] = true;
+        h->pb_consts_ready = true;
     }
     {
         // lists in global memory: one slice per resident warp
         const int smem = OSD_FPB * (int)sizeof(PbHead);
-        static thread_local int occ_g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        int& occ = occ_g[h->device & 7];
+        int& occ = h->occ[OCC_OSD_PB];
         if (occ == 0) {
             LDPCB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, osd_pb_kernel, OSD_THREADS, smem));
             if (occ < 1) occ = 1;
@@ -309,7 +307,7 @@ using namespace ldpcb;
 extern "C" int ldpcb_osd_pb_decode(ldpcb_t* h, const float* llr_dev, int64_t B, int order_limit, float snr_db,
                                    uint32_t* cw_bits_dev, int32_t* stats_dev, int64_t* best_score_q_dev,
                                    int32_t* score_exp_dev, void* stream) {
-    if (!h) return LDPCB_ERR_ARG;
+    LDPCB_ENTER(h);
     if (B < 0 || order_limit < 0 || order_limit > 3)
         return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_pb_decode: B=%lld order_limit=%d out of range (0..3)", (long long)B, order_limit);
     if (B == 0) return LDPCB_OK;
@@ -342,10 +340,9 @@ extern "C" int ldpcb_osd_pb_decode(ldpcb_t* h, const float* llr_dev, int64_t B, 
 
 extern "C" int ldpcb_osd_pb_decode_host(ldpcb_t* h, const float* llr_host, int64_t B, int order_limit, float snr_db,
                                         uint32_t* cw_bits_host, int32_t* stats_host) {
-    if (!h) return LDPCB_ERR_ARG;
+    LDPCB_ENTER(h);
     if (B < 0 || !llr_host || !cw_bits_host) return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_pb_decode_host: bad arguments");
     if (B == 0) return LDPCB_OK;
-    LDPCB_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = h->streams[0];
     const int64_t chunk = 1 << 16;
     const size_t need = 256 * 4 + (size_t)chunk * (N * sizeof(float) + 16 + 16);

@@ -105,7 +105,7 @@ extern "C" int ldpcb_decode(ldpcb_t* h, const float* llr_dev, int64_t B, int ite
                             float w_marg, int early_stop, int osd_order, int tep_order, uint32_t* final_bits_dev,
                             uint8_t* syndrome_nz_dev, int32_t* best_tep_dev, const uint32_t* truth_bits_dev,
                             uint64_t* counters_dev, void* stream) {
-    if (!h) return LDPCB_ERR_ARG;
+    LDPCB_ENTER(h);
     DecodeParams p{iters, alpha_check, w_vc, w_marg, early_stop, osd_order, tep_order};
     int s = check_decode_params(h, "ldpcb_decode", B, p);
     if (s != LDPCB_OK) return s;
@@ -113,8 +113,9 @@ extern "C" int ldpcb_decode(ldpcb_t* h, const float* llr_dev, int64_t B, int ite
     if (!llr_dev || !final_bits_dev) return set_error(h, LDPCB_ERR_ARG, "ldpcb_decode: NULL llr or final_bits");
     if ((uintptr_t)llr_dev & 15) return set_error(h, LDPCB_ERR_ALIGN, "ldpcb_decode: llr must be 16-byte aligned");
     DecodeWs probe = carve_decode(nullptr, 0, B);
-    if ((s = ensure_ws(h, 0, probe.bytes)) != LDPCB_OK) return s;
-    DecodeWs w = carve_decode(h->ws[0].buf, 0, B);
+    char* wsbuf = nullptr;
+    if ((s = ensure_stream_ws(h, (cudaStream_t)stream, probe.bytes, &wsbuf)) != LDPCB_OK) return s;
+    DecodeWs w = carve_decode(wsbuf, 0, B);
     return decode_on_device(h, w, llr_dev, B, p, final_bits_dev, syndrome_nz_dev, best_tep_dev, truth_bits_dev,
                             counters_dev, (cudaStream_t)stream);
 }
@@ -122,7 +123,7 @@ extern "C" int ldpcb_decode(ldpcb_t* h, const float* llr_dev, int64_t B, int ite
 extern "C" int ldpcb_simulate(ldpcb_t* h, uint64_t seed, uint64_t first_frame, int64_t B, float ebn0_db, int iters,
                               float alpha_check, float w_vc, float w_marg, int early_stop, int osd_order,
                               int tep_order, uint64_t* counters_dev, void* stream) {
-    if (!h) return LDPCB_ERR_ARG;
+    LDPCB_ENTER(h);
     DecodeParams p{iters, alpha_check, w_vc, w_marg, early_stop, osd_order, tep_order};
     int s = check_decode_params(h, "ldpcb_simulate", B, p);
     if (s != LDPCB_OK) return s;
@@ -135,13 +136,14 @@ extern "C" int ldpcb_simulate(ldpcb_t* h, uint64_t seed, uint64_t first_frame, i
     c.take<int32_t>((size_t)B);
     const size_t head = c.off;
     DecodeWs probe = carve_decode(nullptr, head, B);
-    if ((s = ensure_ws(h, 0, probe.bytes)) != LDPCB_OK) return s;
-    Carver d(h->ws[0].buf);
+    char* wsbuf = nullptr;
+    if ((s = ensure_stream_ws(h, (cudaStream_t)stream, probe.bytes, &wsbuf)) != LDPCB_OK) return s;
+    Carver d(wsbuf);
     float* llr = d.take<float>((size_t)B * N);
     uint32_t* truth = d.take<uint32_t>((size_t)B * 4);
     uint32_t* bits = d.take<uint32_t>((size_t)B * 4);
     int32_t* best = d.take<int32_t>((size_t)B);
-    DecodeWs w = carve_decode(h->ws[0].buf, head, B);
+    DecodeWs w = carve_decode(wsbuf, head, B);
     cudaStream_t st = (cudaStream_t)stream;
     if ((s = launch_gen(h, seed, first_frame, B, ebn0_db, llr, truth, st)) != LDPCB_OK) return s;
     return decode_on_device(h, w, llr, B, p, bits, nullptr, best, truth, counters_dev, st);
@@ -162,11 +164,10 @@ static int sync_streams(ldpcb_handle* h) {
 extern "C" int ldpcb_nms_decode_host(ldpcb_t* h, const float* llr_host, int64_t B, int iters, float alpha_check,
                                      float w_vc, float w_marg, int early_stop, uint32_t* hard_bits_host,
                                      uint8_t* iters_used_host, uint8_t* syndrome_nz_host, float* soft_traj_host) {
-    if (!h) return LDPCB_ERR_ARG;
+    LDPCB_ENTER(h);
     if (B < 0 || iters < 0 || iters > LDPCB_MAX_ITERS) return set_error(h, LDPCB_ERR_ARG, "ldpcb_nms_decode_host: B=%lld iters=%d out of range", (long long)B, iters);
     if (B == 0) return LDPCB_OK;
     if (!llr_host || !hard_bits_host) return set_error(h, LDPCB_ERR_ARG, "ldpcb_nms_decode_host: NULL llr or hard_bits");
-    LDPCB_CUDA(h, cudaSetDevice(h->device));
     const int rows = iters + 1;
     const int64_t chunk = soft_traj_host ? std::min<int64_t>(HOST_CHUNK, 1 << 14) : HOST_CHUNK;
     int ci = 0;
@@ -202,12 +203,11 @@ extern "C" int ldpcb_osd_decode_host(ldpcb_t* h, const float* order_llr_host, co
                                      int order, int tep_order, int flags, uint32_t* cw_bits_host,
                                      int32_t* best_tep_host, int64_t* best_score_q_host, int32_t* score_exp_host,
                                      uint8_t* perm_host, uint64_t* redG_host) {
-    if (!h) return LDPCB_ERR_ARG;
+    LDPCB_ENTER(h);
     if (B < 0 || order < 0 || order > 3 || tep_order < 0 || tep_order > 1 || (flags & ~3))
         return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_decode_host: B=%lld order=%d tep_order=%d flags=%d out of range", (long long)B, order, tep_order, flags);
     if (B == 0) return LDPCB_OK;
     if (!order_llr_host || !score_llr_host || !cw_bits_host) return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_decode_host: NULL llr or cw_bits");
-    LDPCB_CUDA(h, cudaSetDevice(h->device));
     const bool same = (order_llr_host == score_llr_host);
     const TepTable& t = h->tep[order][tep_order];
     int ci = 0;
@@ -251,12 +251,11 @@ extern "C" int ldpcb_osd_sweep_host(ldpcb_t* h, const float* upd_order_llr_host,
                                     const uint64_t* redG_host, int64_t B, const uint32_t* teps_host, int32_t n_teps, int flags,
                                     uint32_t* cw_bits_host, int32_t* best_tep_host, int64_t* best_score_q_host,
                                     int32_t* score_exp_host) {
-    if (!h) return LDPCB_ERR_ARG;
+    LDPCB_ENTER(h);
     if (B < 0 || n_teps < 1 || (flags & ~3)) return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_sweep_host: B=%lld n_teps=%d flags=%d out of range", (long long)B, n_teps, flags);
     if (B == 0) return LDPCB_OK;
     if (!upd_order_llr_host || !upd_score_llr_host || !redG_host || !teps_host || !cw_bits_host)
         return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_sweep_host: NULL argument");
-    LDPCB_CUDA(h, cudaSetDevice(h->device));
     const bool same = (upd_order_llr_host == upd_score_llr_host);
     int maxw = 1;
     for (int i = 0; i < n_teps; ++i) {
@@ -307,11 +306,10 @@ extern "C" int ldpcb_osd_sweep_host(ldpcb_t* h, const float* upd_order_llr_host,
 extern "C" int ldpcb_osd_fs_decode_host(ldpcb_t* h, const float* llr_host, int64_t B, int order_limit, float tau_e, int tau_psc,
                                         float beta_shift, uint32_t* cw_bits_host, int32_t* best_tep_host,
                                         int32_t* num_teps_host, uint8_t* stop_kind_host) {
-    if (!h) return LDPCB_ERR_ARG;
+    LDPCB_ENTER(h);
     if (B < 0 || order_limit < 0 || order_limit > 3) return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_fs_decode_host: bad arguments");
     if (B == 0) return LDPCB_OK;
     if (!llr_host || !cw_bits_host) return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_fs_decode_host: NULL llr or cw_bits");
-    LDPCB_CUDA(h, cudaSetDevice(h->device));
     int ci = 0;
     for (int64_t b0 = 0; b0 < B; b0 += HOST_CHUNK, ++ci) {
         const int64_t nb = std::min(HOST_CHUNK, B - b0);
@@ -343,13 +341,12 @@ extern "C" int ldpcb_decode_host(ldpcb_t* h, const float* llr_host, int64_t B, i
                                  float w_marg, int early_stop, int osd_order, int tep_order,
                                  uint32_t* final_bits_host, uint8_t* syndrome_nz_host, int32_t* best_tep_host,
                                  const uint32_t* truth_bits_host, uint64_t* counters_host) {
-    if (!h) return LDPCB_ERR_ARG;
+    LDPCB_ENTER(h);
     DecodeParams p{iters, alpha_check, w_vc, w_marg, early_stop, osd_order, tep_order};
     int s = check_decode_params(h, "ldpcb_decode_host", B, p);
     if (s != LDPCB_OK) return s;
     if (B == 0) return LDPCB_OK;
     if (!llr_host || !final_bits_host) return set_error(h, LDPCB_ERR_ARG, "ldpcb_decode_host: NULL llr or final_bits");
-    LDPCB_CUDA(h, cudaSetDevice(h->device));
     const bool tally = truth_bits_host && counters_host;
     // device counters live at the head of workspace slot 0
     if ((s = ensure_ws(h, 0, 4096)) != LDPCB_OK) return s;
