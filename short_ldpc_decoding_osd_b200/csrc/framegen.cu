@@ -11,32 +11,9 @@
 //   stream 1, block 0: words x0 | x1<<32 -> the 64 message bits
 #include "common.cuh"
 #include "internal.cuh"
+#include "philox.cuh"
 
 namespace ldpcb {
-
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-    const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const unsigned hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
-        const unsigned hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-        k.x += W0;
-        k.y += W1;
-    }
-    return c;
-}
-
-// u in (0,1): 23 random bits + 1/2, exactly representable in fp32
-__device__ __forceinline__ float u01(unsigned x) { return ((float)(x >> 9) + 0.5f) * 1.1920928955078125e-07f; }
-
-__device__ __forceinline__ void box_muller(unsigned a, unsigned b, float& z0, float& z1) {
-    const float r = sqrtf(-2.0f * logf(u01(a)));
-    float s, c;
-    sincospif(2.0f * u01(b), &s, &c);
-    z0 = r * c;
-    z1 = r * s;
-}
 
 constexpr int GEN_WARPS = 8;
 
@@ -50,23 +27,15 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) gen_frames_kernel(uint2 key, u
     for (int i = 0; i < 4; ++i) g[i] = gcol[4 * lane + i];
     for (int64_t f = gw; f < B; f += nw) {
         const uint64_t fr = first_frame + (uint64_t)f;
-        const unsigned flo = (unsigned)fr, fhi = (unsigned)(fr >> 32);
         // message bits (computed by every lane: cheaper than a broadcast of two words + divergence)
-        const uint4 mw = philox4x32_10(make_uint4(flo, fhi, 0u, 1u), key);
-        const unsigned long long msg = (unsigned long long)mw.x | ((unsigned long long)mw.y << 32);
+        const unsigned long long msg = gen_message(key, fr);
         unsigned nib = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) nib |= (unsigned)(__popcll(msg & g[i]) & 1) << i;
         if (llr) {
-            const uint4 x = philox4x32_10(make_uint4(flo, fhi, (unsigned)lane, 0u), key);
-            float z[4];
-            box_muller(x.x, x.y, z[0], z[1]);
-            box_muller(x.z, x.w, z[2], z[3]);
-            float4 y;
-            y.x = __fmaf_rn(sigma, z[0], 1.0f);
-            y.y = __fmaf_rn(sigma, z[1], 1.0f);
-            y.z = __fmaf_rn(sigma, z[2], 1.0f);
-            y.w = __fmaf_rn(sigma, z[3], 1.0f);
+            float yy[4];
+            gen_block(key, fr, (unsigned)lane, sigma, yy);
+            float4 y = make_float4(yy[0], yy[1], yy[2], yy[3]);
             if (nib & 1u) y.x = -y.x;
             if (nib & 2u) y.y = -y.y;
             if (nib & 4u) y.z = -y.z;
@@ -86,8 +55,7 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) gen_frames_kernel(uint2 key, u
 int launch_gen(ldpcb_handle* h, uint64_t seed, uint64_t first_frame, int64_t B, float ebn0_db, float* llr,
                uint32_t* cw_bits, cudaStream_t st) {
     if (B == 0) return LDPCB_OK;
-    const double rate = (double)K / (double)N;
-    const float sigma = (float)sqrt(1.0 / (2.0 * rate * pow(10.0, (double)ebn0_db / 10.0)));
+    const float sigma = ebn0_to_sigma(ebn0_db);
     int64_t want = (B + GEN_WARPS - 1) / GEN_WARPS;
     int64_t cap = (int64_t)h->sm_count * 8;
     const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
