@@ -67,8 +67,8 @@ struct Workspace {
     size_t cap = 0;
 };
 // slots of ldpcb_handle::occ (occupancy is a property of (kernel, device), so it lives in the handle)
-enum { OCC_NMS = 0 /* +0..7: template variants */, OCC_NMS_QC = 8 /* +0..3 */, OCC_OSD = 12 /* +0..9 */, OCC_OSD_FS = 22, OCC_OSD_PAIR = 23,
-       OCC_OSD_PB = 24, OCC_OSD3 = 25, OCC_SIM = 26 /* +0..1 */, OCC_SLOTS = 32 };
+enum { OCC_NMS = 0 /* +0..7: template variants */, OCC_NMS_QC = 8 /* +0..4 */, OCC_OSD = 13 /* +0..8 */, OCC_OSD_FS = 23, OCC_OSD_PAIR = 24,
+       OCC_OSD_PB = 25, OCC_OSD3 = 26, OCC_SLOTS = 32 };
 
 }  // namespace ldpcb
 
@@ -87,6 +87,7 @@ struct ldpcb_handle {
     ldpcb::Workspace ws[ldpcb::NUM_WS];   // [1..3]: the *_host pipelines' private slots, [0]: their shared counters
     std::map<cudaStream_t, ldpcb::Workspace> stream_ws;  // scratch of the device-pointer calls, one per caller stream
     int occ[ldpcb::OCC_SLOTS] = {};       // resident CTAs per SM of each kernel variant on THIS handle's device (0 = not queried)
+    bool qc_ccsds = false;                // H is the CCSDS (128,64) matrix nms_qc.cu is specialised to
     bool pb_consts_ready = false;         // __constant__ tables of osd_pb.cu uploaded to this device
     char* pb_list = nullptr;       // PB-OSD order 3: TEP lists of the resident warps
     size_t pb_list_cap = 0;        // in list entries
@@ -156,6 +157,26 @@ struct NmsArgs {
 };
 int launch_nms(ldpcb_handle* h, const NmsArgs& a, cudaStream_t st);
 
+// Work fused into the quasi-cyclic NMS kernel (nms_qc.cu) by the device pipelines: tallies, the list of frames that go
+// to OSD, and -- for the Monte-Carlo step -- the frame generator in front of the decoder.
+struct NmsFuse {
+    const uint32_t* truth = nullptr;   // [B,4] transmitted codewords (NULL and !gen: no tally)
+    uint64_t* counters = nullptr;      // LDPCB_CNT_* block, accumulated
+    int32_t* fail_idx = nullptr;       // frames with a non-zero syndrome, in completion order (not sorted)
+    int32_t* fail_count = nullptr;     // zeroed by the caller before the launch
+    int osd_follows = 0;               // 1: detected failures are tallied as final by the OSD kernel, not here
+    int gen = 0;                       // 1: generate frame first_frame + f instead of loading a.llr
+    uint2 key = {0u, 0u};
+    uint64_t first_frame = 0;
+    float sigma = 0.0f;
+    const uint64_t* gcol = nullptr;
+    float* fail_llr = nullptr;         // gen: [*,128] channel LLRs of the appended frames, row = position in fail_idx
+    uint32_t* fail_truth = nullptr;    // gen: [*,4] their transmitted codewords
+};
+bool nms_qc_matches_code(const uint8_t* H);
+bool nms_qc_applies(const ldpcb_handle* h, const NmsArgs& a);
+int launch_nms_qc(ldpcb_handle* h, const NmsArgs& a, const NmsFuse* fuse, cudaStream_t st);
+
 struct OsdArgs {
     const float* order_llr;
     const float* score_llr;
@@ -180,6 +201,10 @@ struct OsdArgs {
     int32_t* block_arg;
     const uint32_t* truth_bits;
     int64_t* truth_score_q;
+    // fused tallies of the device pipelines (ldpcb_decode / ldpcb_simulate): decisions are compared with the transmitted
+    // codewords in the output step and the LDPCB_CNT_OSD_* / FINAL_* / TEPS / PHASE counters accumulated by the kernel
+    const uint32_t* tally_truth;   // [.,4]: row = the frame's original index (idx given) or its position in the batch
+    uint64_t* tally_counters;
 };
 int launch_osd(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st);
 int launch_osd_pair(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st);  // order 2, full lists: warp-local tensor-core pair sweep

@@ -249,6 +249,7 @@ static int launch_deg(ldpcb_handle* h, const NmsArgs& a, cudaStream_t st) {
 
 int launch_nms(ldpcb_handle* h, const NmsArgs& a, cudaStream_t st) {
     if (a.B == 0) return LDPCB_OK;
+    if (nms_qc_applies(h, a)) return launch_nms_qc(h, a, nullptr, st);  // CCSDS (128,64): half-warp-per-frame shuffle kernel (nms_qc.cu)
     bool reg8 = true;
     for (int c = 0; c < M; ++c) reg8 = reg8 && h->nms_host.chk_var[c][DC - 1] < N;
     if (reg8 && h->nms_host.max_var_deg_lo <= 5 && h->nms_host.max_var_deg_hi <= 3) return launch_deg<5, 3, true>(h, a, st);

@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_kernel(OsdArgs a, const ui
     const int64_t nframes = a.count ? (int64_t)*a.count : a.B;
     const bool ties_high = (a.flags & LDPCB_OSD_TIES_HIGH_INDEX_FIRST) != 0;
     const bool disc_from_score = (a.flags & LDPCB_OSD_DISC_HARD_FROM_SCORE) != 0;
+    OsdTally tally;
 
     for (int64_t f0 = (int64_t)blockIdx.x * OSD_FPB; f0 < nframes; f0 += (int64_t)gridDim.x * OSD_FPB) {
         const int64_t f = f0 + warp;
@@ -264,10 +265,9 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_kernel(OsdArgs a, const ui
 #pragma unroll
                 for (int k = 0; k < 4; ++k) wout[k] = __ballot_sync(0xffffffffu, F.pos[lane + 32 * k]);
                 const int64_t orow = a.idx ? row : f;
-                if (lane < 4 && a.cw_bits) {
-                    const unsigned wv = lane == 0 ? wout[0] : lane == 1 ? wout[1] : lane == 2 ? wout[2] : wout[3];
-                    a.cw_bits[orow * 4 + lane] = wv;
-                }
+                const unsigned wv = lane == 0 ? wout[0] : lane == 1 ? wout[1] : lane == 2 ? wout[2] : wout[3];
+                if (lane < 4 && a.cw_bits) a.cw_bits[orow * 4 + lane] = wv;
+                if (a.tally_truth) osd_tally_frame(tally, a, orow, wv, best_i, lane);
                 if (lane == 0) {
                     if (a.best_tep) a.best_tep[orow] = best_i;
                     if (a.best_score_q) a.best_score_q[orow] = best_s;
@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_kernel(OsdArgs a, const ui
         // the next round's prepare overwrites fr[] and red_*: every warp has passed the barrier above and
         // only touches its own FrameSm until the next barrier
     }
+    if (!BLOCKS && a.tally_truth) osd_tally_flush(tally, a, lane);
 }
 
 

@@ -8,6 +8,36 @@ namespace ldpcb {
 constexpr int OSD_WIN = 72;       // >= 64 LRB terms + 4 MRB terms + 1 base term
 constexpr int OSD_CAND_CAP = 16;
 
+// ---- fused tallies (convention_osd.py:67-75 success test and phase; get_eval-style error counts) ----------------------
+struct OsdTally {
+    unsigned frames = 0, fe = 0, be = 0, ph[4] = {0u, 0u, 0u, 0u};
+};
+// wv: this lane's word of the decided codeword (lanes 0..3), trow: row of the transmitted codeword
+__device__ __forceinline__ void osd_tally_frame(OsdTally& t, const OsdArgs& a, int64_t trow, unsigned wv, int best_i, int lane) {
+    unsigned d = 0;
+    if (lane < 4) d = __popc(wv ^ __ldg(a.tally_truth + trow * 4 + lane));
+    d = __reduce_add_sync(0xffffffffu, d);
+    t.frames += 1;
+    t.fe += d != 0;
+    t.be += d;
+    if (d == 0) {  // weight class of the winning TEP: boundaries 1, 65, 2081 in both enumerations (convention_osd.py:39-47)
+        const int w = best_i < 1 ? 0 : best_i < 65 ? 1 : best_i < 2081 ? 2 : 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t.ph[i] += (w == i);
+    }
+}
+__device__ __forceinline__ void osd_tally_flush(const OsdTally& t, const OsdArgs& a, int lane) {
+    if (lane != 0 || t.frames == 0) return;
+    unsigned long long* c = reinterpret_cast<unsigned long long*>(a.tally_counters);
+    atomicAdd(c + LDPCB_CNT_OSD_FRAMES, (unsigned long long)t.frames);
+    atomicAdd(c + LDPCB_CNT_TEPS, (unsigned long long)t.frames * (unsigned long long)a.n_teps);
+    if (t.fe) { atomicAdd(c + LDPCB_CNT_OSD_FRAME_ERR, (unsigned long long)t.fe); atomicAdd(c + LDPCB_CNT_FINAL_FRAME_ERR, (unsigned long long)t.fe); }
+    if (t.be) { atomicAdd(c + LDPCB_CNT_OSD_BIT_ERR, (unsigned long long)t.be); atomicAdd(c + LDPCB_CNT_FINAL_BIT_ERR, (unsigned long long)t.be); }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (t.ph[i]) atomicAdd(c + LDPCB_CNT_PHASE0 + i, (unsigned long long)t.ph[i]);
+}
+
 // lut[b][x] = sum of q_lrb[8b+i] over the set bits i of x; thread: table b, low nibble fixed
 __device__ __forceinline__ void build_lut64(unsigned long long (*lut)[256], const FrameSm& G, int tid) {
     const int b = tid >> 4, lo = tid & 15;

@@ -11,6 +11,7 @@
 
 #include "common.cuh"
 #include "internal.cuh"
+#include "philox.cuh"
 
 namespace ldpcb {
 
@@ -89,6 +90,63 @@ static int decode_on_device(ldpcb_handle* h, const DecodeWs& w, const float* llr
     return LDPCB_OK;
 }
 
+// ---- fused pipeline (CCSDS code, fixed iteration count): two kernels ----------------------------------------------
+// nms_qc_kernel<FUSE> decodes, tallies the NMS stage and appends the frames with a non-zero syndrome to a list (in
+// completion order: OSD results are written by frame index, so the order is immaterial); the OSD kernel reads the
+// list and its length from device memory and tallies its own decisions.  No select / tally kernels, no host sync.
+static bool fused_applies(const ldpcb_handle* h, const DecodeParams& p) {
+    return h->qc_ccsds && p.early_stop == 0 && p.iters >= 1 && p.w_vc == p.w_marg;
+}
+
+struct FusedWs {
+    int32_t* count;
+    int32_t* idx;
+    float* fail_llr;       // simulate only
+    uint32_t* fail_truth;  // simulate only
+    size_t bytes;
+};
+static FusedWs carve_fused(char* base, int64_t B, bool gen) {
+    Carver c(base);
+    FusedWs w;
+    w.count = c.take<int32_t>(64);
+    w.idx = c.take<int32_t>((size_t)B);
+    w.fail_llr = gen ? c.take<float>((size_t)B * N) : nullptr;
+    w.fail_truth = gen ? c.take<uint32_t>((size_t)B * 4) : nullptr;
+    w.bytes = c.off + 256;
+    return w;
+}
+
+static int osd_after_nms(ldpcb_handle* h, const FusedWs& w, const float* llr, bool compact, int64_t B, const DecodeParams& p,
+                         uint32_t* final_bits, int32_t* best_tep, const uint32_t* truth, uint64_t* counters, cudaStream_t st) {
+    const TepTable& t = h->tep[p.osd_order][p.tep_order];
+    OsdArgs a = {};
+    a.order_llr = llr; a.score_llr = llr; a.idx = compact ? nullptr : w.idx; a.count = w.count; a.B = B;
+    a.teps = t.dev; a.n_teps = t.n; a.maxw = t.maxw; a.pair_index = t.pair_dev; a.flags = 0;
+    a.cw_bits = final_bits; a.best_tep = best_tep;
+    a.tally_truth = (truth && counters) ? truth : nullptr; a.tally_counters = counters;
+    return launch_osd(h, a, st);
+}
+
+static int decode_fused(ldpcb_handle* h, const FusedWs& w, const float* llr, int64_t B, const DecodeParams& p,
+                        uint32_t* final_bits, uint8_t* syn_out, int32_t* best_tep, const uint32_t* truth,
+                        uint64_t* counters, cudaStream_t st) {
+    const bool tally = truth && counters;
+    LDPCB_CUDA(h, cudaMemsetAsync(w.count, 0, sizeof(int32_t), st));
+    if (best_tep) LDPCB_CUDA(h, cudaMemsetAsync(best_tep, 0xFF, sizeof(int32_t) * (size_t)B, st));
+    NmsArgs n;
+    n.llr = llr; n.idx = nullptr; n.B = B; n.iters = p.iters;
+    n.alpha = p.alpha; n.w_vc = p.w_vc; n.w_marg = p.w_marg; n.early_stop = 0;
+    n.hard_bits = final_bits; n.iters_used = nullptr; n.syndrome_nz = syn_out; n.soft_traj = nullptr;
+    NmsFuse z;
+    z.truth = tally ? truth : nullptr; z.counters = tally ? counters : nullptr;
+    z.osd_follows = p.osd_order >= 0;
+    if (p.osd_order >= 0) { z.fail_idx = w.idx; z.fail_count = w.count; }
+    int s = launch_nms_qc(h, n, &z, st);
+    if (s != LDPCB_OK) return s;
+    if (p.osd_order >= 0) s = osd_after_nms(h, w, llr, false, B, p, final_bits, best_tep, truth, counters, st);
+    return s;
+}
+
 static int check_decode_params(ldpcb_handle* h, const char* fn, int64_t B, const DecodeParams& p) {
     if (B < 0 || B > 0x7fffffff) return set_error(h, LDPCB_ERR_ARG, "%s: B=%lld out of range", fn, (long long)B);
     if (p.iters < 0 || p.iters > LDPCB_MAX_ITERS) return set_error(h, LDPCB_ERR_ARG, "%s: iters=%d out of range", fn, p.iters);
@@ -112,8 +170,13 @@ extern "C" int ldpcb_decode(ldpcb_t* h, const float* llr_dev, int64_t B, int ite
     if (B == 0) return LDPCB_OK;
     if (!llr_dev || !final_bits_dev) return set_error(h, LDPCB_ERR_ARG, "ldpcb_decode: NULL llr or final_bits");
     if ((uintptr_t)llr_dev & 15) return set_error(h, LDPCB_ERR_ALIGN, "ldpcb_decode: llr must be 16-byte aligned");
-    DecodeWs probe = carve_decode(nullptr, 0, B);
     char* wsbuf = nullptr;
+    if (fused_applies(h, p)) {
+        if ((s = ensure_stream_ws(h, (cudaStream_t)stream, carve_fused(nullptr, B, false).bytes, &wsbuf)) != LDPCB_OK) return s;
+        return decode_fused(h, carve_fused(wsbuf, B, false), llr_dev, B, p, final_bits_dev, syndrome_nz_dev, best_tep_dev, truth_bits_dev,
+                            counters_dev, (cudaStream_t)stream);
+    }
+    DecodeWs probe = carve_decode(nullptr, 0, B);
     if ((s = ensure_stream_ws(h, (cudaStream_t)stream, probe.bytes, &wsbuf)) != LDPCB_OK) return s;
     DecodeWs w = carve_decode(wsbuf, 0, B);
     return decode_on_device(h, w, llr_dev, B, p, final_bits_dev, syndrome_nz_dev, best_tep_dev, truth_bits_dev,
@@ -129,6 +192,27 @@ extern "C" int ldpcb_simulate(ldpcb_t* h, uint64_t seed, uint64_t first_frame, i
     if (s != LDPCB_OK) return s;
     if (B == 0) return LDPCB_OK;
     if (!counters_dev) return set_error(h, LDPCB_ERR_ARG, "ldpcb_simulate: NULL counters");
+    if (fused_applies(h, p)) {
+        // generator fused into the decoder's prologue: no LLR ever reaches HBM except the channel values of the frames
+        // NMS could not fix (512 B each), which the kernel appends for the OSD stage together with their codewords
+        cudaStream_t st = (cudaStream_t)stream;
+        char* wsbuf = nullptr;
+        if ((s = ensure_stream_ws(h, st, carve_fused(nullptr, B, true).bytes, &wsbuf)) != LDPCB_OK) return s;
+        const FusedWs w = carve_fused(wsbuf, B, true);
+        LDPCB_CUDA(h, cudaMemsetAsync(w.count, 0, sizeof(int32_t), st));
+        NmsArgs n;
+        n.llr = nullptr; n.idx = nullptr; n.B = B; n.iters = p.iters;
+        n.alpha = p.alpha; n.w_vc = p.w_vc; n.w_marg = p.w_marg; n.early_stop = 0;
+        n.hard_bits = nullptr; n.iters_used = nullptr; n.syndrome_nz = nullptr; n.soft_traj = nullptr;
+        NmsFuse z;
+        z.counters = counters_dev; z.osd_follows = p.osd_order >= 0; z.gen = 1;
+        z.key = make_uint2((unsigned)seed, (unsigned)(seed >> 32)); z.first_frame = first_frame; z.sigma = ebn0_to_sigma(ebn0_db);
+        z.gcol = h->gcol_dev;
+        if (p.osd_order >= 0) { z.fail_count = w.count; z.fail_llr = w.fail_llr; z.fail_truth = w.fail_truth; }
+        if ((s = launch_nms_qc(h, n, &z, st)) != LDPCB_OK) return s;
+        if (p.osd_order >= 0) s = osd_after_nms(h, w, w.fail_llr, true, B, p, nullptr, nullptr, w.fail_truth, counters_dev, st);
+        return s;
+    }
     Carver c(nullptr);
     c.take<float>((size_t)B * N);
     c.take<uint32_t>((size_t)B * 4);
@@ -377,8 +461,13 @@ extern "C" int ldpcb_decode_host(ldpcb_t* h, const float* llr_host, int64_t B, i
         DecodeWs w = carve_decode(h->ws[slot].buf, head, nb);
         LDPCB_CUDA(h, cudaMemcpyAsync(llr, llr_host + b0 * N, sizeof(float) * nb * N, cudaMemcpyHostToDevice, st));
         if (tally) LDPCB_CUDA(h, cudaMemcpyAsync(truth, truth_bits_host + b0 * 4, sizeof(uint32_t) * nb * 4, cudaMemcpyHostToDevice, st));
-        s = decode_on_device(h, w, llr, nb, p, bits, syn, (best_tep_host || tally) ? bt : nullptr, tally ? truth : nullptr,
-                             tally ? counters : nullptr, st);
+        if (fused_applies(h, p)) {
+            const FusedWs fw{w.count, w.idx, nullptr, nullptr, 0};
+            s = decode_fused(h, fw, llr, nb, p, bits, syn, best_tep_host ? bt : nullptr, tally ? truth : nullptr, tally ? counters : nullptr, st);
+        } else {
+            s = decode_on_device(h, w, llr, nb, p, bits, syn, (best_tep_host || tally) ? bt : nullptr, tally ? truth : nullptr,
+                                 tally ? counters : nullptr, st);
+        }
         if (s != LDPCB_OK) return s;
         LDPCB_CUDA(h, cudaMemcpyAsync(final_bits_host + b0 * 4, bits, sizeof(uint32_t) * nb * 4, cudaMemcpyDeviceToHost, st));
         if (syndrome_nz_host) LDPCB_CUDA(h, cudaMemcpyAsync(syndrome_nz_host + b0, syn, (size_t)nb, cudaMemcpyDeviceToHost, st));

@@ -1,0 +1,164 @@
+"""-m gpu: the quasi-cyclic NMS kernel (csrc/nms_qc.cu, half a warp per frame, shuffle exchanges) against the
+table-driven kernel (csrc/nms.cu) and the oracle, and the fused device pipelines against their unfused composition.
+Everything through the C ABI; float outputs are compared BIT FOR BIT (both kernels restate the reference's fp32
+operations in the same order: ms_test.py:124-137,180-228)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle as CO
+from oracle import philox_oracle as PO
+from short_ldpc_decoding_osd_b200 import _lib
+from tests.gpu_util import dev, empty, nms_gpu, sync
+
+pytestmark = pytest.mark.gpu
+ALPHA = 0.66943514
+
+
+@pytest.fixture(scope="module")
+def generic_handle(code):
+    """A handle whose NMS runs on the table-driven shared-memory kernel and whose pipelines are unfused."""
+    os.environ["LDPCB_NMS_GENERIC"] = "1"
+    try:
+        h = _lib.Handle(code.H, code.G, device=0)
+    finally:
+        del os.environ["LDPCB_NMS_GENERIC"]
+    yield h
+    h.close()
+
+
+def _edge_frames(code, B, seed):
+    y, cw, _ = PO.gen_frames(seed, 0, B, 2.5, code.G)
+    y = y.copy()
+    y[0] = 0.0                      # tf.sign(0) = 0 zeroes whole checks
+    y[1, :9] = 0.0
+    y[2] *= 1e20                    # clip at 1e30 after a few iterations
+    y[3] *= 1e-30                   # denormal messages
+    y[4] = -0.0
+    y[5] = np.where(cw[5] == 0, 1.0, -1.0)
+    y[6, ::3] = np.float32(1e-45)
+    return y, cw
+
+
+@pytest.mark.parametrize("B", [1, 2, 3, 33, 1187, 70001])
+def test_qc_kernel_equals_generic_kernel_bit_for_bit(handle, generic_handle, code, B):
+    y, _ = _edge_frames(code, max(B, 8), 11)
+    y = y[:B]
+    traj = B <= 1187
+    a = nms_gpu(handle, y, traj=traj)
+    b = nms_gpu(generic_handle, y, traj=traj)
+    assert np.array_equal(a["hard"], b["hard"])
+    assert np.array_equal(a["syndrome_nz"], b["syndrome_nz"])
+    assert np.array_equal(a["iters_used"], b["iters_used"])
+    if traj:
+        assert np.array_equal(a["traj"].view(np.uint32), b["traj"].view(np.uint32)), "posteriors differ in some bit"
+
+
+def test_qc_kernel_equals_oracle(handle, code):
+    y, _ = _edge_frames(code, 3000, 5)
+    g = nms_gpu(handle, y, traj=True)
+    ref = CO.nms(y, code.H, 12, ALPHA, traj=True)
+    assert np.array_equal(g["hard"], ref["hard"])
+    assert np.array_equal(g["syndrome_nz"], ref["syndrome_nz"])
+    assert np.array_equal(g["traj"].view(np.uint32), ref["traj"].view(np.uint32))
+
+
+def test_qc_kernel_nms2_weight_and_iteration_counts(handle, generic_handle, code):
+    y, _ = _edge_frames(code, 500, 9)
+    for iters, w in ((1, 1.0), (5, 0.83), (20, 1.25)):
+        a = nms_gpu(handle, y, iters=iters, alpha=0.7, w_vc=w, w_marg=w)
+        b = nms_gpu(generic_handle, y, iters=iters, alpha=0.7, w_vc=w, w_marg=w)
+        assert np.array_equal(a["hard"], b["hard"]) and np.array_equal(a["traj"].view(np.uint32), b["traj"].view(np.uint32))
+        ref = CO.nms(y, code.H, iters, 0.7, w, w, traj=True)
+        assert np.array_equal(a["traj"].view(np.uint32), ref["traj"].view(np.uint32))
+
+
+def test_qc_fir_variant_equals_generic(handle, generic_handle, code):
+    y, _ = _edge_frames(code, 777, 3)
+    taps = np.linspace(-0.3, 0.4, 13).astype(np.float32)
+    out = []
+    for h in (handle, generic_handle):
+        yd = dev(y)
+        bits, syn, met = empty((777, 4), torch.int32), empty((777,), torch.uint8), empty((777, 128), torch.float32)
+        h.call("ldpcb_nms_decode_fir", yd, 777, 12, ALPHA, 1.0, 1.0, taps, 0.05, bits, syn, met, None)
+        sync()
+        out.append((bits.cpu().numpy(), syn.cpu().numpy(), met.cpu().numpy()))
+    for u, v in zip(out[0], out[1]):
+        assert np.array_equal(u.view(np.uint8), v.view(np.uint8))
+
+
+@pytest.mark.parametrize("order,B", [(2, 20001), (1, 4099), (0, 513), (3, 300), (-1, 1000)])
+def test_fused_decode_equals_unfused_pipeline(handle, generic_handle, code, order, B):
+    """ldpcb_decode on the fused path (NMS + tallies + failure list in one kernel, OSD + tallies in the other) gives
+    the same decisions, flags, TEP choices and all 16 counters as the 7-launch pipeline."""
+    y, cw = _edge_frames(code, B, 21)
+    truth = dev(_lib.pack_bits(cw).view(np.int32))
+    res = []
+    for h in (handle, generic_handle):
+        yd = dev(y)
+        bits, syn, bt = empty((B, 4), torch.int32), empty((B,), torch.uint8), empty((B,), torch.int32)
+        cnt = torch.zeros(16, dtype=torch.int64, device="cuda:0")
+        for _ in range(2):  # accumulation
+            h.call("ldpcb_decode", yd, B, 12, ALPHA, 1.0, 1.0, 0, order, 0, bits, syn, bt, truth, cnt, None)
+        sync()
+        res.append((bits.cpu().numpy(), syn.cpu().numpy(), bt.cpu().numpy(), cnt.cpu().numpy()))
+    for name, u, v in zip(("bits", "syndrome", "best_tep", "counters"), res[0], res[1]):
+        assert np.array_equal(u, v), name
+    assert res[0][3][0] == 2 * B
+
+
+def test_fused_decode_without_truth_or_best_tep(handle, generic_handle, code):
+    y, _ = _edge_frames(code, 2500, 2)
+    out = []
+    for h in (handle, generic_handle):
+        yd = dev(y)
+        bits = empty((2500, 4), torch.int32)
+        h.call("ldpcb_decode", yd, 2500, 12, ALPHA, 1.0, 1.0, 0, 2, 1, bits, None, None, None, None, None)
+        sync()
+        out.append(bits.cpu().numpy())
+    assert np.array_equal(out[0], out[1])
+
+
+@pytest.mark.parametrize("order,ebn0,B", [(2, 2.5, 30001), (1, 1.5, 5000), (-1, 3.0, 999)])
+def test_fused_simulate_equals_unfused(handle, generic_handle, order, ebn0, B):
+    """The Monte-Carlo step with the generator fused into the decoder's prologue tallies exactly what
+    generate -> decode -> tally does (same Philox frames, same decisions)."""
+    cs = []
+    for h in (handle, generic_handle):
+        cnt = torch.zeros(16, dtype=torch.int64, device="cuda:0")
+        h.call("ldpcb_simulate", 77, 1 << 40, B, ebn0, 12, ALPHA, 1.0, 1.0, 0, order, 0, cnt, None)
+        sync()
+        cs.append(cnt.cpu().numpy())
+    assert np.array_equal(cs[0], cs[1]), (cs[0], cs[1])
+    assert cs[0][0] == B
+
+
+def test_two_streams_do_not_share_scratch(handle, code):
+    """ldpcb_decode calls of one handle on two streams used to carve the same workspace."""
+    B = 40000
+    y1, c1 = _edge_frames(code, B, 31)
+    y2, c2 = _edge_frames(code, B, 32)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    bufs = []
+    for y, cw, st in ((y1, c1, s1), (y2, c2, s2)):
+        yd, tr = dev(y), dev(_lib.pack_bits(cw).view(np.int32))
+        bits = empty((B, 4), torch.int32)
+        cnt = torch.zeros(16, dtype=torch.int64, device="cuda:0")
+        bufs.append((yd, tr, bits, cnt, st))
+    sync()
+    for rep in range(3):
+        for yd, tr, bits, cnt, st in bufs:
+            handle.call("ldpcb_decode", yd, B, 12, ALPHA, 1.0, 1.0, 0, 2, 0, bits, None, None, tr, cnt, st.cuda_stream)
+    sync()
+    for yd, tr, bits, cnt, st in bufs:
+        outs.append((bits.cpu().numpy().copy(), cnt.cpu().numpy().copy()))
+    # reference: the same calls one after the other on the default stream
+    for (yd, tr, bits, cnt, st), (b_par, c_par) in zip(bufs, outs):
+        cnt.zero_()
+        for rep in range(3):
+            handle.call("ldpcb_decode", yd, B, 12, ALPHA, 1.0, 1.0, 0, 2, 0, bits, None, None, tr, cnt, None)
+        sync()
+        assert np.array_equal(bits.cpu().numpy(), b_par) and np.array_equal(cnt.cpu().numpy(), c_par)
