@@ -91,6 +91,7 @@ struct ldpcb_handle {
     bool pb_consts_ready = false;         // __constant__ tables of osd_pb.cu uploaded to this device
     char* pb_list = nullptr;       // PB-OSD order 3: TEP lists of the resident warps
     size_t pb_list_cap = 0;        // in list entries
+    int* pb_queue = nullptr;       // PB-OSD: work counter of the running launch
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t events[3] = {nullptr, nullptr, nullptr};
     uint64_t launches = 0;
@@ -229,6 +230,7 @@ struct PbParams {
     long long* glist_sum; // order 3: per-warp TEP lists in global memory (set by the launcher)
     long long* glist_bmin; // order 3: minima of every 32 list entries
     unsigned* glist_tep;
+    int* queue;           // next frame to decode (dynamic work distribution; zeroed by the launcher)
 };
 int launch_osd_pb(ldpcb_handle* h, const OsdArgs& a, const PbParams& pp, cudaStream_t st);
 

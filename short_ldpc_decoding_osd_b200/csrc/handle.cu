@@ -374,6 +374,7 @@ int ldpcb_create(ldpcb_t** out, const uint8_t* H_host, const uint8_t* G_host, in
     if ((st = build_tep_tables(h)) != LDPCB_OK) return fail(st);
     h->qc_ccsds = nms_qc_matches_code(h->H) && !getenv("LDPCB_NMS_GENERIC");  // env: force the table-driven kernel (tests, A/B timing)
     if ((st = check_cuda(h, cudaMalloc(&h->one_block_dev, 2 * sizeof(int32_t)), "cudaMalloc")) != LDPCB_OK) return fail(st);
+    if ((st = check_cuda(h, cudaMalloc(&h->pb_queue, 256), "cudaMalloc")) != LDPCB_OK) return fail(st);
     for (int i = 0; i < 3; ++i) {
         if ((st = check_cuda(h, cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking), "cudaStreamCreate")) != LDPCB_OK) return fail(st);
         if ((st = check_cuda(h, cudaEventCreateWithFlags(&h->events[i], cudaEventDisableTiming), "cudaEventCreate")) != LDPCB_OK) return fail(st);
@@ -396,6 +397,7 @@ void ldpcb_destroy(ldpcb_t* h) {
     for (auto& kv : h->stream_ws)
         if (kv.second.buf) cudaFree(kv.second.buf);
     if (h->pb_list) cudaFree(h->pb_list);
+    if (h->pb_queue) cudaFree(h->pb_queue);
     for (int i = 0; i < 3; ++i) {
         if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
         if (h->events[i]) cudaEventDestroy(h->events[i]);

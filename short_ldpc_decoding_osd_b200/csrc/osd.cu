@@ -314,6 +314,8 @@ __device__ __forceinline__ void fs_eval(const OsdSmem& S, const FrameSm& G, unsi
     hd = __popcll(D) + __popcll(flip ^ d0m);
 }
 
+constexpr int FS_CHUNK = 8 * OSD_THREADS;  // 1024 TEPs between two "has anybody stopped?" barriers
+
 __global__ void __launch_bounds__(OSD_THREADS) osd_fs_kernel(OsdArgs a, FsParams fp, const uint64_t* __restrict__ gcol) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     OsdSmem& S = *reinterpret_cast<OsdSmem*>(smem_raw);
@@ -372,53 +374,59 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_fs_kernel(OsdArgs a, FsParams
                     bnd += qv < 0 ? -qv : qv;
                     if (!(bnd + shift_q < w_dmin)) { kind = 2; break; }
                     const int r0 = cls_start[j + 1], r1 = cls_start[j + 2];
+                    // The class is swept in chunks of FS_CHUNK TEPs: the sequential loop of the reference stops at the first
+                    // TEP closer than tau_e, on average after ~600 (order 2) / ~3000 (order 3) of the 2016 / 41664 TEPs of
+                    // the class, so sweeping whole classes to find that TEP wasted most of the work.  A chunk costs one
+                    // barrier (__syncthreads_or: did any thread see a stop?); only the chunk that holds the stop is swept
+                    // twice (the decision must not see the TEPs behind it).
+                    long long pbs = 0x7fffffffffffffffll;  // this thread's best over the completed chunks
+                    int pbi = 0x7fffffff;
                     int first_stop = 0x7fffffff;
-                    long long bs = 0x7fffffffffffffffll;
-                    int bi = 0x7fffffff;
-                    for (int i = r0 + tid; i < r1; i += OSD_THREADS) {
-                        long long s;
-                        int hd;
-                        fs_eval(S, G, __ldg(a.teps + i), gd0, gbase, d0m, s, hd);
-                        if ((float)hd < fp.tau_e) first_stop = min(first_stop, i);
-                        if (hd < fp.tau_psc && s < bs) { bs = s; bi = i; }
-                    }
-                    warp_argmin(bs, bi);
-                    first_stop = __reduce_min_sync(0xffffffffu, first_stop);
-                    __syncthreads();  // previous use of the reduction slots is over
-                    if (lane == 0) { S.red_s[w][warp] = bs; S.red_i[w][warp] = bi; S.red_stop[warp] = first_stop; }
-                    __syncthreads();
-                    first_stop = min(min(S.red_stop[0], S.red_stop[1]), min(S.red_stop[2], S.red_stop[3]));
-                    if (first_stop == 0x7fffffff) {
-                        bs = S.red_s[w][0]; bi = S.red_i[w][0];
-#pragma unroll
-                        for (int v = 1; v < OSD_FPB; ++v) {
-                            const long long os = S.red_s[w][v];
-                            const int oi = S.red_i[w][v];
-                            if (os < bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
-                        }
-                        if (bs < w_dmin) { w_dmin = bs; opt = bi; }
-                        num += r1 - r0;
-                    } else {
-                        // second pass: the decision only sees the TEPs before the stopping one
-                        bs = 0x7fffffffffffffffll; bi = 0x7fffffff;
-                        for (int i = r0 + tid; i < first_stop; i += OSD_THREADS) {
+                    for (int c0 = r0; c0 < r1; c0 += FS_CHUNK) {
+                        const int c1 = c0 + FS_CHUNK < r1 ? c0 + FS_CHUNK : r1;
+                        long long cbs = 0x7fffffffffffffffll;
+                        int cbi = 0x7fffffff, fst = 0x7fffffff;
+                        for (int i = c0 + tid; i < c1; i += OSD_THREADS) {
                             long long s;
                             int hd;
                             fs_eval(S, G, __ldg(a.teps + i), gd0, gbase, d0m, s, hd);
-                            if (hd < fp.tau_psc && s < bs) { bs = s; bi = i; }
+                            if ((float)hd < fp.tau_e) fst = min(fst, i);
+                            if (hd < fp.tau_psc && s < cbs) { cbs = s; cbi = i; }
                         }
-                        warp_argmin(bs, bi);
-                        __syncthreads();
-                        if (lane == 0) { S.red_s[w][warp] = bs; S.red_i[w][warp] = bi; }
-                        __syncthreads();
-                        bs = S.red_s[w][0]; bi = S.red_i[w][0];
+                        if (__syncthreads_or(fst != 0x7fffffff)) {
+                            fst = __reduce_min_sync(0xffffffffu, fst);
+                            if (lane == 0) S.red_stop[warp] = fst;
+                            __syncthreads();
+                            first_stop = min(min(S.red_stop[0], S.red_stop[1]), min(S.red_stop[2], S.red_stop[3]));
+                            cbs = 0x7fffffffffffffffll; cbi = 0x7fffffff;
+                            for (int i = c0 + tid; i < first_stop; i += OSD_THREADS) {
+                                long long s;
+                                int hd;
+                                fs_eval(S, G, __ldg(a.teps + i), gd0, gbase, d0m, s, hd);
+                                if (hd < fp.tau_psc && s < cbs) { cbs = s; cbi = i; }
+                            }
+                            if (cbs < pbs) { pbs = cbs; pbi = cbi; }
+                            break;
+                        }
+                        if (cbs < pbs) { pbs = cbs; pbi = cbi; }
+                    }
+                    long long bs = pbs;
+                    int bi = pbi;
+                    warp_argmin(bs, bi);
+                    __syncthreads();  // previous use of the reduction slots is over
+                    if (lane == 0) { S.red_s[w][warp] = bs; S.red_i[w][warp] = bi; }
+                    __syncthreads();
+                    bs = S.red_s[w][0]; bi = S.red_i[w][0];
 #pragma unroll
-                        for (int v = 1; v < OSD_FPB; ++v) {
-                            const long long os = S.red_s[w][v];
-                            const int oi = S.red_i[w][v];
-                            if (os < bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
-                        }
-                        if (bs < w_dmin) { w_dmin = bs; opt = bi; }
+                    for (int v = 1; v < OSD_FPB; ++v) {
+                        const long long os = S.red_s[w][v];
+                        const int oi = S.red_i[w][v];
+                        if (os < bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
+                    }
+                    if (bs < w_dmin) { w_dmin = bs; opt = bi; }
+                    if (first_stop == 0x7fffffff) {
+                        num += r1 - r0;
+                    } else {
                         num += first_stop - r0 + 1;
                         kind = 1;
                         break;

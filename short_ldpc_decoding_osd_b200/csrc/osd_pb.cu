@@ -61,11 +61,15 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_pb_kernel(OsdArgs a, PbParams
     };
     FrameSm& F = W.fr;
     const int64_t nframes = a.count ? (int64_t)*a.count : a.B;
-    const int64_t gw = (int64_t)blockIdx.x * OSD_FPB + warp;
-    const int64_t nw = (int64_t)gridDim.x * OSD_FPB;
     const int n_max = pp.order <= 0 ? 1 : (pp.order == 1 ? 65 : (pp.order == 2 ? 2081 : 43745));
 
-    for (int64_t f = gw; f < nframes; f += nw) {
+    // frames are handed out one at a time from a device counter: a frame takes between a handful and N_max - 1 TEPs
+    // (mean ~100-200, maximum 43,744 at order 3), so a static split leaves most warps idle behind the slowest one
+    for (;;) {
+        int fq = 0;
+        if (lane == 0) fq = atomicAdd(pp.queue, 1);
+        const int64_t f = (int64_t)__shfl_sync(0xffffffffu, fq, 0);
+        if (f >= nframes) break;
         const int64_t row = a.idx ? (int64_t)a.idx[f] : f;
         __syncwarp();
         Prep P = prepare_frame<false>(a, F, gcol, row, f, lane, false, false);
@@ -291,6 +295,8 @@ int launch_osd_pb(ldpcb_handle* h, const OsdArgs& a, const PbParams& pp, cudaStr
             h->pb_list_cap = per;
         }
         PbParams q = pp;
+        q.queue = h->pb_queue;
+        LDPCB_CUDA(h, cudaMemsetAsync(h->pb_queue, 0, sizeof(int), st));
         q.glist_sum = reinterpret_cast<long long*>(h->pb_list);
         q.glist_bmin = reinterpret_cast<long long*>(h->pb_list + per * sizeof(long long));
         q.glist_tep = reinterpret_cast<unsigned*>(h->pb_list + per * sizeof(long long) + per / 32 * sizeof(long long));

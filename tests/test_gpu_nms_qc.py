@@ -29,6 +29,14 @@ def generic_handle(code):
     h.close()
 
 
+def _same_floats(a, b):
+    """Exact equality of fp32 values; the only bit patterns allowed to differ are the signs of zeros (the kernels carry
+    the sign product through a zeroed check, the oracle multiplies by tf.sign(0) = 0: both are zero messages)."""
+    ua, ub = np.ascontiguousarray(a).view(np.uint32), np.ascontiguousarray(b).view(np.uint32)
+    diff = ua != ub
+    return bool(np.all(a[diff] == 0.0) and np.all(b[diff] == 0.0))
+
+
 def _edge_frames(code, B, seed):
     y, cw, _ = PO.gen_frames(seed, 0, B, 2.5, code.G)
     y = y.copy()
@@ -62,7 +70,7 @@ def test_qc_kernel_equals_oracle(handle, code):
     ref = CO.nms(y, code.H, 12, ALPHA, traj=True)
     assert np.array_equal(g["hard"], ref["hard"])
     assert np.array_equal(g["syndrome_nz"], ref["syndrome_nz"])
-    assert np.array_equal(g["traj"].view(np.uint32), ref["traj"].view(np.uint32))
+    assert _same_floats(g["traj"], ref["traj"])
 
 
 def test_qc_kernel_nms2_weight_and_iteration_counts(handle, generic_handle, code):
@@ -72,7 +80,7 @@ def test_qc_kernel_nms2_weight_and_iteration_counts(handle, generic_handle, code
         b = nms_gpu(generic_handle, y, iters=iters, alpha=0.7, w_vc=w, w_marg=w)
         assert np.array_equal(a["hard"], b["hard"]) and np.array_equal(a["traj"].view(np.uint32), b["traj"].view(np.uint32))
         ref = CO.nms(y, code.H, iters, 0.7, w, w, traj=True)
-        assert np.array_equal(a["traj"].view(np.uint32), ref["traj"].view(np.uint32))
+        assert _same_floats(a["traj"], ref["traj"])
 
 
 def test_qc_fir_variant_equals_generic(handle, generic_handle, code):
