@@ -5,6 +5,10 @@ and the tests read the fixtures.
 
     python oracle/ref_runner.py all          # regenerate every fixture (a few minutes)
     python oracle/ref_runner.py nms|osd|fs|pb|dl|gf2|gen
+    python oracle/ref_runner.py nms --real-tf --out /tmp/g   # same run under a REAL TensorFlow (no shim on sys.path),
+                                                             # fixture written to /tmp/g: tests/test_tf_ready.py diffs
+                                                             # it against the committed shim fixture
+The reference tree is /root/reference, or $LDPCB_REFERENCE_ROOT.
 
 Each sub-command runs in its own process with sys.path = [oracle/tf_shim, <one reference directory>]
 because the reference's directories all define modules with the same names (globalmap, fill_matrix_info,
@@ -25,14 +29,16 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-REF = "/root/reference/LDPC_128"
+REF = os.path.join(os.environ.get("LDPCB_REFERENCE_ROOT", "/root/reference"), "LDPC_128")
 GOLD = os.path.join(ROOT, "tests", "golden")
+REAL_TF = False
 ALIST = "CCSDS_ldpc_n128_k64.alist"
 
 
 def _enter(refdir: str):
     sys.path.insert(0, os.path.join(REF, refdir))
-    sys.path.insert(0, os.path.join(HERE, "tf_shim"))
+    if not REAL_TF:
+        sys.path.insert(0, os.path.join(HERE, "tf_shim"))
     os.chdir(tempfile.mkdtemp(prefix="refrun_"))  # the reference writes ./log/*.txt relative to cwd
 
 
@@ -376,10 +382,14 @@ CMDS = {"gen": run_gen, "nms": run_nms, "osd": run_osd, "fs": run_fs, "pb": run_
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if "--real-tf" in sys.argv:
+        REAL_TF = True
+    if "--out" in sys.argv:
+        GOLD = os.path.abspath(sys.argv[sys.argv.index("--out") + 1])
     os.makedirs(GOLD, exist_ok=True)
     if which == "all":
         for name in ("gen", "gf2", "nms", "osd", "fs", "pb", "dl"):
             print("==", name, flush=True)
-            subprocess.run([sys.executable, os.path.abspath(__file__), name], check=True)
+            subprocess.run([sys.executable, os.path.abspath(__file__), name] + sys.argv[2:], check=True)
     else:
         CMDS[which]()
