@@ -365,6 +365,21 @@ int ldpcb_decode_host(ldpcb_t* h, const float* llr_host, int64_t B, int iters, f
                       uint32_t* final_bits_host, uint8_t* syndrome_nz_host, int32_t* best_tep_host,
                       const uint32_t* truth_bits_host, uint64_t* counters_host);
 
+/*
+ * Decoding_model.call in one call (Ldpc_128_testing/ms_test.py:30-34): NMS on every frame with the get_eval tallies
+ * (:36-54) and the iters+1 posteriors of the frames left with a non-zero syndrome, ascending frame order -- the
+ * 13-rows-per-failure retest records of collect_failed_output_selective (:55-64).  The failures are compacted and
+ * re-decoded on the device; the host pays one H2D copy and D2H copies sized by the failure count.
+ *   truth_bits_host [B,4] and counters_host [LDPCB_NUM_COUNTERS] (both or neither; counters accumulate)
+ *   hard_bits_host [B,4] out, syndrome_nz_host [B] out (may be NULL)
+ *   fail_idx_host [max_fail] out: frame indices; fail_traj_host [max_fail, iters+1, 128] out: row 0 = input
+ *   n_fail_host out: number of frames with a non-zero syndrome (may exceed max_fail; only the first max_fail are stored)
+ */
+int ldpcb_nms_retest_host(ldpcb_t* h, const float* llr_host, int64_t B, int iters, float alpha_check, float w_vc,
+                          float w_marg, const uint32_t* truth_bits_host, uint32_t* hard_bits_host,
+                          uint8_t* syndrome_nz_host, uint64_t* counters_host, int64_t max_fail,
+                          int32_t* fail_idx_host, float* fail_traj_host, int64_t* n_fail_host);
+
 /* PCI bus id ("0000:1b:00.0") of a CUDA device, for callers that bind their host threads and pinned buffers to the
  * GPU's NUMA node (/sys/bus/pci/devices/<id>/numa_node) before ldpcb_host_alloc's first touch.  len >= 13. */
 int ldpcb_device_pci_bus_id(int device, char* buf, int len);

@@ -55,6 +55,7 @@ SYMBOLS = {
     "ldpcb_osd_fs_decode_host": (_i32, [_vp, _vp, _i64, _i32, _f32, _i32, _f32, _vp, _vp, _vp, _vp]),
     "ldpcb_osd_pb_decode": (_i32, [_vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
     "ldpcb_osd_pb_decode_host": (_i32, [_vp, _vp, _i64, _i32, _f32, _vp, _vp]),
+    "ldpcb_nms_retest_host": (_i32, [_vp, _vp, _i64, _i32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "ldpcb_decode_host": (_i32, [_vp, _vp, _i64, _i32, _f32, _f32, _f32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "ldpcb_device_pci_bus_id": (_i32, [_i32, C.c_char_p, _i32]),
     "ldpcb_host_alloc": (_i32, [C.POINTER(_vp), _u64]),

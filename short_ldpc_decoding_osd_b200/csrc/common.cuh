@@ -59,6 +59,7 @@ struct TepTable {
     // orders 0..2: inverse of the enumeration, [i*64+j] (i<j) -> index of the pair TEP, [4096+i] -> index of the
     // single TEP {i}, [4096+64] -> index of the empty TEP (the tensor-core pair sweep visits TEPs in its own order)
     uint16_t* pair_dev = nullptr;
+    uint16_t* triple_dev = nullptr;  // order 3: inverse of the enumeration for the weight-3 TEPs, [C(k,3)+C(j,2)+i] for i<j<k
 };
 constexpr int OSD_PAIR_TABLE = 64 * 64 + 65;
 
@@ -85,6 +86,7 @@ struct ldpcb_handle {
     ldpcb::TepTable tep[4][2];      // [order][tep_order]
     int32_t* one_block_dev = nullptr;  // {0, n} scratch for single-block calls
     ldpcb::Workspace ws[ldpcb::NUM_WS];   // [1..3]: the *_host pipelines' private slots, [0]: their shared counters
+    std::map<cudaStream_t, ldpcb::Workspace> fb_ws;      // osd3.cu: frames left to the exact sweep, one list per caller stream
     std::map<cudaStream_t, ldpcb::Workspace> stream_ws;  // scratch of the device-pointer calls, one per caller stream
     int occ[ldpcb::OCC_SLOTS] = {};       // resident CTAs per SM of each kernel variant on THIS handle's device (0 = not queried)
     bool qc_ccsds = false;                // H is the CCSDS (128,64) matrix nms_qc.cu is specialised to
@@ -188,6 +190,7 @@ struct OsdArgs {
     const uint32_t* teps;
     int n_teps;
     int maxw;
+    const uint16_t* triple_index;  // order-3 tables: [C(k,3) + C(j,2) + i] (i<j<k) -> index of the triple TEP (osd3.cu)
     const uint16_t* pair_index;  // optional (full order-0/1/2 tables): selects the warp-local sweep (orders 0, 1) or the tensor-core pair sweep (order 2)
     const int32_t* block_start;  // NULL => one block [0,n_teps)
     int n_blocks;
@@ -208,7 +211,8 @@ struct OsdArgs {
     uint64_t* tally_counters;
 };
 int launch_osd(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st);
-int launch_osd_pair(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st);  // order 2, full lists: warp-local tensor-core pair sweep
+int launch_osd_pair(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st);
+int launch_osd3(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st);      // order 3, full lists: tensor-core sweep of the 62 pair problems (osd3.cu)  // order 2, full lists: warp-local tensor-core pair sweep
 
 // FS-OSD policy parameters (FS_OSD/fs_testing.py:92,129-160)
 struct FsParams {

@@ -119,14 +119,20 @@ int build_tep_tables(ldpcb_handle* h) {
             padded.resize(t.n + 128, 0xFFFFFFFFu);
             LDPCB_CUDA(h, cudaMalloc(&t.dev, sizeof(uint32_t) * padded.size()));
             LDPCB_CUDA(h, cudaMemcpy(t.dev, padded.data(), sizeof(uint32_t) * padded.size(), cudaMemcpyHostToDevice));
-            if (order <= 2) {
+            {
                 std::vector<uint16_t> inv(OSD_PAIR_TABLE, 0xFFFFu);
+                std::vector<uint16_t> inv3(K * (K - 1) * (K - 2) / 6, 0xFFFFu);
                 for (int i = 0; i < t.n; ++i) {
                     const uint32_t v = t.host[i];
-                    const unsigned a = v & 0xFFu, b = (v >> 8) & 0xFFu;
+                    const unsigned a = v & 0xFFu, b = (v >> 8) & 0xFFu, c = (v >> 16) & 0xFFu;
                     if (a >= (unsigned)K) inv[K * K + K] = (uint16_t)i;
                     else if (b >= (unsigned)K) inv[K * K + a] = (uint16_t)i;
-                    else inv[a * K + b] = (uint16_t)i;
+                    else if (c >= (unsigned)K) inv[a * K + b] = (uint16_t)i;
+                    else inv3[c * (c - 1) * (c - 2) / 6 + b * (b - 1) / 2 + a] = (uint16_t)i;  // positions ascend: a < b < c
+                }
+                if (order == 3) {
+                    LDPCB_CUDA(h, cudaMalloc(&t.triple_dev, sizeof(uint16_t) * inv3.size()));
+                    LDPCB_CUDA(h, cudaMemcpy(t.triple_dev, inv3.data(), sizeof(uint16_t) * inv3.size(), cudaMemcpyHostToDevice));
                 }
                 LDPCB_CUDA(h, cudaMalloc(&t.pair_dev, sizeof(uint16_t) * inv.size()));
                 LDPCB_CUDA(h, cudaMemcpy(t.pair_dev, inv.data(), sizeof(uint16_t) * inv.size(), cudaMemcpyHostToDevice));
@@ -391,10 +397,13 @@ void ldpcb_destroy(ldpcb_t* h) {
         for (int kd = 0; kd < 2; ++kd) {
             if (h->tep[o][kd].dev) cudaFree(h->tep[o][kd].dev);
             if (h->tep[o][kd].pair_dev) cudaFree(h->tep[o][kd].pair_dev);
+            if (h->tep[o][kd].triple_dev) cudaFree(h->tep[o][kd].triple_dev);
         }
     for (int i = 0; i < NUM_WS; ++i)
         if (h->ws[i].buf) cudaFree(h->ws[i].buf);
     for (auto& kv : h->stream_ws)
+        if (kv.second.buf) cudaFree(kv.second.buf);
+    for (auto& kv : h->fb_ws)
         if (kv.second.buf) cudaFree(kv.second.buf);
     if (h->pb_list) cudaFree(h->pb_list);
     if (h->pb_queue) cudaFree(h->pb_queue);

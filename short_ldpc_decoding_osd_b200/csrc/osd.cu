@@ -30,6 +30,8 @@
 //   5c. block minima (DL path), FS policy and the near-tie fallback: exact 64-bit scores through byte LUTs
 //   6. the TEPs within the truncation window of the minimum are re-scored exactly; lexicographic
 //      (score, index) minimum = first minimum in enumeration order (tf.argmin)
+#include <cstdlib>
+
 #include "common.cuh"
 #include "osd_prepare.cuh"
 #include "osd_sweep.cuh"
@@ -514,6 +516,8 @@ static int launch_variant(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st) {
     return LDPCB_OK;
 }
 
+int launch_osd_generic3(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st) { return launch_variant<3, false>(h, a, st); }
+
 int launch_osd(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st) {
     if (a.B == 0) return LDPCB_OK;
     const bool blocks = a.block_start != nullptr;
@@ -525,7 +529,10 @@ int launch_osd(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st) {
             if (blocks) return launch_variant<2, true>(h, a, st);
             if (a.pair_index && a.n_teps == 2081) return launch_osd_pair(h, a, st);  // osd_pair.cu
             return launch_variant<2, false>(h, a, st);
-        case 3: return blocks ? launch_variant<3, true>(h, a, st) : launch_variant<3, false>(h, a, st);
+        case 3:
+            if (blocks) return launch_variant<3, true>(h, a, st);
+            if (a.pair_index && a.triple_index && a.n_teps == 43745 && !a.redG_in && !getenv("LDPCB_OSD3_GENERIC")) return launch_osd3(h, a, st);  // osd3.cu
+            return launch_variant<3, false>(h, a, st);
         default: return blocks ? launch_variant<4, true>(h, a, st) : launch_variant<4, false>(h, a, st);
     }
 }
@@ -554,7 +561,7 @@ extern "C" int ldpcb_osd_decode(ldpcb_t* h, const float* order_llr_dev, const fl
     const TepTable& t = h->tep[order][tep_order];
     OsdArgs a = {};
     a.order_llr = order_llr_dev; a.score_llr = score_llr_dev; a.B = B;
-    a.teps = t.dev; a.n_teps = t.n; a.maxw = t.maxw; a.pair_index = t.pair_dev; a.flags = flags;
+    a.teps = t.dev; a.n_teps = t.n; a.maxw = t.maxw; a.pair_index = t.pair_dev; a.triple_index = t.triple_dev; a.flags = flags;
     a.cw_bits = cw_bits_dev; a.best_tep = best_tep_dev; a.best_score_q = best_score_q_dev;
     a.score_exp = score_exp_dev; a.perm = perm_dev; a.redG = redG_dev;
     return launch_osd(h, a, (cudaStream_t)stream);

@@ -78,7 +78,7 @@ static int decode_on_device(ldpcb_handle* h, const DecodeWs& w, const float* llr
         const TepTable& t = h->tep[p.osd_order][p.tep_order];
         OsdArgs a = {};
         a.order_llr = llr; a.score_llr = llr; a.idx = w.idx; a.count = w.count; a.B = B;
-        a.teps = t.dev; a.n_teps = t.n; a.maxw = t.maxw; a.pair_index = t.pair_dev; a.flags = 0;
+        a.teps = t.dev; a.n_teps = t.n; a.maxw = t.maxw; a.pair_index = t.pair_dev; a.triple_index = t.triple_dev; a.flags = 0;
         a.cw_bits = final_bits; a.best_tep = best_tep;
         s = launch_osd(h, a, st);
         if (s != LDPCB_OK) return s;
@@ -121,7 +121,7 @@ static int osd_after_nms(ldpcb_handle* h, const FusedWs& w, const float* llr, bo
     const TepTable& t = h->tep[p.osd_order][p.tep_order];
     OsdArgs a = {};
     a.order_llr = llr; a.score_llr = llr; a.idx = compact ? nullptr : w.idx; a.count = w.count; a.B = B;
-    a.teps = t.dev; a.n_teps = t.n; a.maxw = t.maxw; a.pair_index = t.pair_dev; a.flags = 0;
+    a.teps = t.dev; a.n_teps = t.n; a.maxw = t.maxw; a.pair_index = t.pair_dev; a.triple_index = t.triple_dev; a.flags = 0;
     a.cw_bits = final_bits; a.best_tep = best_tep;
     a.tally_truth = (truth && counters) ? truth : nullptr; a.tally_counters = counters;
     return launch_osd(h, a, st);
@@ -317,7 +317,7 @@ extern "C" int ldpcb_osd_decode_host(ldpcb_t* h, const float* order_llr_host, co
         LDPCB_CUDA(h, cudaMemcpyAsync(ol, order_llr_host + b0 * N, sizeof(float) * nb * N, cudaMemcpyHostToDevice, st));
         if (!same) LDPCB_CUDA(h, cudaMemcpyAsync(sl, score_llr_host + b0 * N, sizeof(float) * nb * N, cudaMemcpyHostToDevice, st));
         OsdArgs a = {};
-        a.order_llr = ol; a.score_llr = same ? ol : sl; a.B = nb; a.teps = t.dev; a.n_teps = t.n; a.maxw = t.maxw; a.pair_index = t.pair_dev; a.flags = flags;
+        a.order_llr = ol; a.score_llr = same ? ol : sl; a.B = nb; a.teps = t.dev; a.n_teps = t.n; a.maxw = t.maxw; a.pair_index = t.pair_dev; a.triple_index = t.triple_dev; a.flags = flags;
         a.cw_bits = bits; a.best_tep = bt; a.best_score_q = bq; a.score_exp = ex;
         a.perm = perm_host ? pm : nullptr; a.redG = redG_host ? rg : nullptr;
         if ((s = launch_osd(h, a, st)) != LDPCB_OK) return s;
@@ -479,5 +479,90 @@ extern "C" int ldpcb_decode_host(ldpcb_t* h, const float* llr_host, int64_t B, i
         LDPCB_CUDA(h, cudaMemcpy(tmp, counters, sizeof tmp, cudaMemcpyDeviceToHost));
         for (int i = 0; i < LDPCB_NUM_COUNTERS; ++i) counters_host[i] += tmp[i];
     }
+    return LDPCB_OK;
+}
+
+// Decoding_model.call in one host call (ms_test.py:30-34): NMS on every frame with the get_eval tallies (:36-54), then the
+// iters+1 posteriors of the frames with a non-zero syndrome, in ascending frame order -- the 13-row retest records of
+// collect_failed_output_selective (:55-64).  The failures are compacted on the device and re-decoded there with the
+// trajectory output (a few hundred frames), so the host sees one H2D copy, one small synchronisation for the failure
+// count, and D2H copies sized by that count.
+extern "C" int ldpcb_nms_retest_host(ldpcb_t* h, const float* llr_host, int64_t B, int iters, float alpha_check, float w_vc,
+                                     float w_marg, const uint32_t* truth_bits_host, uint32_t* hard_bits_host,
+                                     uint8_t* syndrome_nz_host, uint64_t* counters_host, int64_t max_fail,
+                                     int32_t* fail_idx_host, float* fail_traj_host, int64_t* n_fail_host) {
+    LDPCB_ENTER(h);
+    if (B < 0 || B > 0x7fffffff || iters < 0 || iters > LDPCB_MAX_ITERS || max_fail < 0)
+        return set_error(h, LDPCB_ERR_ARG, "ldpcb_nms_retest_host: B=%lld iters=%d max_fail=%lld out of range", (long long)B, iters, (long long)max_fail);
+    if (!n_fail_host) return set_error(h, LDPCB_ERR_ARG, "ldpcb_nms_retest_host: NULL n_fail");
+    *n_fail_host = 0;
+    if (B == 0) return LDPCB_OK;
+    if (!llr_host || !hard_bits_host || (max_fail > 0 && (!fail_idx_host || !fail_traj_host)))
+        return set_error(h, LDPCB_ERR_ARG, "ldpcb_nms_retest_host: NULL llr, hard_bits, fail_idx or fail_traj");
+    const bool tally = truth_bits_host && counters_host;
+    const int rows = iters + 1;
+    const int64_t chunk = std::min<int64_t>(B, 1 << 14);
+    cudaStream_t st = h->streams[0];
+    int s;
+    Carver probe(nullptr);
+    probe.take<uint64_t>(LDPCB_NUM_COUNTERS); probe.take<float>((size_t)chunk * N); probe.take<uint32_t>((size_t)chunk * 4);
+    probe.take<uint32_t>((size_t)chunk * 4); probe.take<uint32_t>((size_t)chunk * 4); probe.take<float>((size_t)chunk * rows * N);
+    const size_t head = probe.off;
+    DecodeWs pw = carve_decode(nullptr, head, chunk);
+    if ((s = ensure_ws(h, 1, pw.bytes)) != LDPCB_OK) return s;
+    Carver c(h->ws[1].buf);
+    uint64_t* counters = c.take<uint64_t>(LDPCB_NUM_COUNTERS);
+    float* llr = c.take<float>((size_t)chunk * N);
+    uint32_t* bits = c.take<uint32_t>((size_t)chunk * 4);
+    uint32_t* truth = c.take<uint32_t>((size_t)chunk * 4);
+    uint32_t* bits2 = c.take<uint32_t>((size_t)chunk * 4);
+    float* traj = c.take<float>((size_t)chunk * rows * N);
+    DecodeWs w = carve_decode(h->ws[1].buf, head, chunk);
+    if (tally) LDPCB_CUDA(h, cudaMemsetAsync(counters, 0, sizeof(uint64_t) * LDPCB_NUM_COUNTERS, st));
+    int64_t total_fail = 0, stored = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+        const int64_t nb = std::min(chunk, B - b0);
+        LDPCB_CUDA(h, cudaMemcpyAsync(llr, llr_host + b0 * N, sizeof(float) * nb * N, cudaMemcpyHostToDevice, st));
+        if (tally) LDPCB_CUDA(h, cudaMemcpyAsync(truth, truth_bits_host + b0 * 4, sizeof(uint32_t) * nb * 4, cudaMemcpyHostToDevice, st));
+        NmsArgs n;
+        n.llr = llr; n.idx = nullptr; n.B = nb; n.iters = iters; n.alpha = alpha_check; n.w_vc = w_vc; n.w_marg = w_marg; n.early_stop = 0;
+        n.hard_bits = bits; n.iters_used = w.iters; n.syndrome_nz = w.syn; n.soft_traj = nullptr;
+        if (nms_qc_applies(h, n)) {
+            NmsFuse z;
+            z.truth = tally ? truth : nullptr; z.counters = tally ? counters : nullptr;
+            n.iters_used = nullptr;
+            s = launch_nms_qc(h, n, &z, st);
+        } else {
+            s = launch_nms(h, n, st);
+            if (s == LDPCB_OK && tally) s = launch_tally_nms(h, bits, w.syn, w.iters, truth, nb, counters, st);
+            if (s == LDPCB_OK && tally) s = launch_tally_final(h, bits, nullptr, nullptr, -1, 0, truth, nb, counters, st);
+        }
+        if (s != LDPCB_OK) return s;
+        if ((s = launch_select(h, w.syn, nb, w.idx, w.count, w.sel_temp, st)) != LDPCB_OK) return s;
+        int32_t nf = 0;
+        LDPCB_CUDA(h, cudaMemcpyAsync(&nf, w.count, sizeof nf, cudaMemcpyDeviceToHost, st));
+        LDPCB_CUDA(h, cudaMemcpyAsync(hard_bits_host + b0 * 4, bits, sizeof(uint32_t) * nb * 4, cudaMemcpyDeviceToHost, st));
+        if (syndrome_nz_host) LDPCB_CUDA(h, cudaMemcpyAsync(syndrome_nz_host + b0, w.syn, (size_t)nb, cudaMemcpyDeviceToHost, st));
+        LDPCB_CUDA(h, cudaStreamSynchronize(st));
+        total_fail += nf;
+        const int64_t take = std::min<int64_t>(nf, max_fail - stored);
+        if (take > 0) {
+            NmsArgs t = n;
+            t.idx = w.idx; t.B = take; t.hard_bits = bits2; t.iters_used = nullptr; t.syndrome_nz = nullptr; t.soft_traj = traj;
+            if ((s = launch_nms(h, t, st)) != LDPCB_OK) return s;
+            LDPCB_CUDA(h, cudaMemcpyAsync(fail_idx_host + stored, w.idx, sizeof(int32_t) * take, cudaMemcpyDeviceToHost, st));
+            LDPCB_CUDA(h, cudaMemcpyAsync(fail_traj_host + stored * rows * N, traj, sizeof(float) * take * rows * N, cudaMemcpyDeviceToHost, st));
+            LDPCB_CUDA(h, cudaStreamSynchronize(st));
+            for (int64_t i = 0; i < take; ++i) fail_idx_host[stored + i] += (int32_t)b0;
+            stored += take;
+        }
+    }
+    if (tally) {
+        uint64_t tmp[LDPCB_NUM_COUNTERS];
+        LDPCB_CUDA(h, cudaMemcpyAsync(tmp, counters, sizeof tmp, cudaMemcpyDeviceToHost, st));
+        LDPCB_CUDA(h, cudaStreamSynchronize(st));
+        for (int i = 0; i < LDPCB_NUM_COUNTERS; ++i) counters_host[i] += tmp[i];
+    }
+    *n_fail_host = total_fail;
     return LDPCB_OK;
 }

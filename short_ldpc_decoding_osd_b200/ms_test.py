@@ -73,6 +73,47 @@ class Decoder_Layer:
         return [traj[:, i, :] for i in range(self.num_iterations + 1)]
 
 
+class _Rows:
+    """Read-only sequence of the rows of a 2-D array (optionally row i -> base[index[i]]): what the reference builds as
+    a Python list of 13*F tensors (ms_test.py:55-64), without materialising 13*F objects.  len(), iteration, indexing
+    and np.asarray() behave like the list of rows; `.array()` returns the stacked rows (a view when possible)."""
+
+    def __init__(self, base: np.ndarray, index: np.ndarray = None):
+        self._base, self._index = base, index
+
+    def __len__(self):
+        return len(self._base) if self._index is None else len(self._index)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        return self._base[i] if self._index is None else self._base[self._index[i]]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def array(self) -> np.ndarray:
+        return self._base if self._index is None else self._base[self._index]
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.array()
+        return a if dtype is None else a.astype(dtype)
+
+    def __add__(self, other):  # list concatenation, as the reference's drivers do with the per-batch buffers
+        return list(self) + list(other)
+
+    def __radd__(self, other):
+        return list(other) + list(self)
+
+
+def _pack_labels(lab: np.ndarray) -> np.ndarray:
+    """int[B,128] 0/1 labels -> uint32[B,4] (one cast, one packbits)."""
+    b = lab if lab.dtype == np.uint8 else lab.astype(np.uint8)
+    return np.packbits(np.ascontiguousarray(b), axis=1, bitorder="little").view("<u4")
+
+
 class Decoding_model:
     def __init__(self):
         self.layer = Decoder_Layer()
@@ -81,47 +122,45 @@ class Decoding_model:
         return self.call(inputs, labels)
 
     def call(self, inputs, labels):
-        """One NMS pass with tallies on the GPU, then a second pass that only re-decodes the detected
-        failures to collect their 13-row trajectories (the retest record of ms_test.py:55-64)."""
+        """One C-ABI call (ldpcb_nms_retest_host): NMS with the get_eval tallies on the GPU, the detected failures
+        compacted and re-decoded with trajectory output on the device, their 13 rows copied back -- the retest
+        records of ms_test.py:55-64.  The buffer is returned as two row sequences backed by one array each."""
         y = _as_llr(inputs)
         lab = np.asarray(labels)
         B = y.shape[0]
         L = self.layer
         alpha, w_vc, w_marg = L.kernel_weights()
         h = get_handle(L.code)
-        truth = _lib.pack_bits(lab)
+        rows = L.num_iterations + 1
+        truth = _pack_labels(lab)
         bits = np.empty((B, 4), np.uint32)
         syn = np.empty(B, np.uint8)
         cnt = np.zeros(_lib.NUM_COUNTERS, np.uint64)
-        h.call("ldpcb_decode_host", y, B, L.num_iterations, alpha, w_vc, w_marg, 0, -1, 0, bits, syn, None, truth, cnt)
+        cap = self._fail_cap if getattr(self, "_fail_cap", 0) else max(64, B // 2)
+        while True:
+            fidx = np.empty(cap, np.int32)
+            traj = np.empty((cap, rows, 128), np.float32)
+            nf = np.zeros(1, np.int64)
+            cnt[:] = 0
+            h.call("ldpcb_nms_retest_host", y, B, L.num_iterations, alpha, w_vc, w_marg, truth, bits, syn, cnt, cap, fidx, traj, nf)
+            n = int(nf[0])
+            if n <= cap:
+                break
+            cap = n  # more failures than the buffer held (low SNR): once more with room for all of them
+        self._fail_cap = max(cap, 64)
         fer = float(cnt[1]) / B
         ber = float(cnt[2]) / (B * lab.shape[1])
         undetected = int(cnt[4])
         if undetected:
             und = np.flatnonzero((syn == 0) & (bits != truth).any(axis=1))
             print("Undetected Elements:", und[:, None])
-        indices = np.flatnonzero(syn)[:, None].astype(np.int64)
         self.last_hard_bits = bits
         self.last_counters = cnt
-        buffer = self._collect(y, lab, indices)
-        return fer, ber, undetected, buffer
-
-    def _collect(self, y, lab, indices):
-        L = self.layer
-        idx = indices[:, 0]
-        buffer_inputs, buffer_labels = [], []
-        if len(idx):
-            alpha, w_vc, w_marg = L.kernel_weights()
-            h = get_handle(L.code)
-            yf = np.ascontiguousarray(y[idx])
-            traj = np.empty((len(idx), L.num_iterations + 1, 128), np.float32)
-            bits = np.empty((len(idx), 4), np.uint32)
-            h.call("ldpcb_nms_decode_host", yf, len(idx), L.num_iterations, alpha, w_vc, w_marg, 0, bits, None, None, traj)
-            # the reference's layout (ms_test.py:60-63): for each failure its 13 rows, the label repeated 13 times
-            rows = L.num_iterations + 1
-            buffer_inputs = list(traj.reshape(-1, traj.shape[-1]))
-            buffer_labels = [r for r in lab[idx] for _ in range(rows)]  # 13 references to one row, no copies
-        return buffer_inputs, buffer_labels
+        self.last_index = fidx[:n].astype(np.int64)[:, None]
+        # the reference's layout (ms_test.py:60-63): for each failure its 13 rows, the label repeated 13 times
+        buffer_inputs = _Rows(traj[:n].reshape(n * rows, 128))
+        buffer_labels = _Rows(lab, np.repeat(fidx[:n].astype(np.int64), rows))
+        return fer, ber, undetected, (buffer_inputs, buffer_labels)
 
     def get_eval(self, soft_output_list, labels):
         """(FER, BER, n_undetected, index int64[F,1]) from the last soft output (ms_test.py:36-54).
@@ -152,6 +191,8 @@ class Decoding_model:
         return buffer_inputs, buffer_labels
 
     def postprocess_failure_cases(self, buffer):
+        if len(buffer[0]) and all(isinstance(b, _Rows) for b in buffer[0]) and all(isinstance(b, _Rows) for b in buffer[1]):
+            return _Rows(np.concatenate([b.array() for b in buffer[0]])), _Rows(np.concatenate([b.array() for b in buffer[1]]))
         buffer_inputs = [j for i in buffer[0] for j in i]
         buffer_labels = [j for i in buffer[1] for j in i]
         return buffer_inputs, buffer_labels
@@ -165,6 +206,9 @@ def save_decoded_data(updated_buffer, file_dir, snr, log_filename, list_length):
     if len(updated_buffer[0]) == 0:
         info = np.zeros((0, 128), np.float32)
         label = np.zeros((0, 128), np.int64)
+    elif isinstance(updated_buffer[0], _Rows):
+        info = np.asarray(updated_buffer[0].array(), dtype=np.float32)
+        label = np.asarray(updated_buffer[1].array()).astype(np.int64)
     else:
         info = np.stack([np.asarray(b, dtype=np.float32) for b in updated_buffer[0]])
         label = np.stack([np.asarray(b) for b in updated_buffer[1]]).astype(np.int64)

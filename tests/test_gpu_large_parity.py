@@ -36,7 +36,7 @@ def test_nms_200k_frames_bit_exact(handle, code):
     assert np.array_equal(got_e["hard"], ref_e["hard"]) and np.array_equal(got_e["iters_used"], ref_e["iters_used"])
 
 
-@pytest.mark.parametrize("order,n,tep_order,flags", [(1, 40000, 0, 0), (2, 20000, 0, 0), (2, 6000, 1, 1), (3, 600, 0, 0)])
+@pytest.mark.parametrize("order,n,tep_order,flags", [(1, 40000, 0, 0), (2, 20000, 0, 0), (2, 6000, 1, 1), (3, 600, 0, 0), (3, 3000, 1, 1), (3, 1501, 0, 0)])
 def test_osd_many_frames_bit_exact(handle, code, order, n, tep_order, flags):
     y, cw, _ = PO.gen_frames(4242 + order, 0, 6 * n, 2.5, code.G)
     syn = CO.nms(y, code.H, 12, ALPHA)["syndrome_nz"]
@@ -48,7 +48,7 @@ def test_osd_many_frames_bit_exact(handle, code, order, n, tep_order, flags):
         assert np.array_equal(got[k], ref[k]), k
 
 
-@pytest.mark.parametrize("order,n", [(1, 8000), (2, 3000)])
+@pytest.mark.parametrize("order,n", [(1, 8000), (2, 3000), (3, 400)])
 def test_osd_quantised_inputs_many_ties(handle, code, order, n):
     """Every frame has many equal |y|: the exact tie path of the sort and, at order 2, the exact 64-bit fallback
     of the tensor-core pair sweep (many candidates share the truncated minimum), at scale."""
@@ -111,3 +111,37 @@ def test_pair_sweep_equals_lut_sweep_on_a_million_frames(handle, tep_order, ebn0
     assert torch.equal(ex, ex2)
     assert torch.equal(bq, bm[:, 0])
     assert torch.equal(bt, ba[:, 0])
+
+
+def test_order3_tensor_sweep_equals_generic_sweep_on_many_frames(code):
+    """osd3.cu (62 pair problems on IMMA + exact re-scoring) against the generic order-3 kernel (32-bit shuffle-table
+    sweep) on 2^17 frames of a low-SNR batch: decisions, TEP choices and exact scores, both TEP orders, DL flags."""
+    import os
+
+    import torch
+
+    from short_ldpc_decoding_osd_b200 import _lib
+    from tests.gpu_util import dev, empty, sync
+
+    hq = _lib.Handle(code.H, code.G, device=0)
+    n = 1 << 17
+    y = empty((n, 128), torch.float32)
+    y2 = empty((n, 128), torch.float32)
+    hq.call("ldpcb_gen_frames", 5, 0, n, 1.5, y, None, None)
+    hq.call("ldpcb_gen_frames", 6, 0, n, 1.5, y2, None, None)
+    out = {}
+    for tag in ("tensor", "generic"):
+        if tag == "generic":
+            os.environ["LDPCB_OSD3_GENERIC"] = "1"
+        try:
+            for tep_order, flags, ys in ((0, 0, y), (1, 3, y2)):
+                cw, bt, bq = empty((n, 4), torch.int32), empty((n,), torch.int32), empty((n,), torch.int64)
+                hq.call("ldpcb_osd_decode", y, ys, n, 3, tep_order, flags, cw, bt, bq, None, None, None, None)
+                sync()
+                out[(tag, tep_order)] = (cw.cpu().numpy(), bt.cpu().numpy(), bq.cpu().numpy())
+        finally:
+            os.environ.pop("LDPCB_OSD3_GENERIC", None)
+    for tep_order in (0, 1):
+        for u, v, name in zip(out[("tensor", tep_order)], out[("generic", tep_order)], ("codeword", "best_tep", "best_score_q")):
+            assert np.array_equal(u, v), (tep_order, name, int((u != v).sum()))
+    hq.close()

@@ -170,3 +170,27 @@ def test_two_streams_do_not_share_scratch(handle, code):
             handle.call("ldpcb_decode", yd, B, 12, ALPHA, 1.0, 1.0, 0, 2, 0, bits, None, None, tr, cnt, None)
         sync()
         assert np.array_equal(bits.cpu().numpy(), b_par) and np.array_equal(cnt.cpu().numpy(), c_par)
+
+
+@pytest.mark.parametrize("B,cap", [(1000, 1000), (20000, 25000), (3000, 40)])
+def test_retest_host_equals_decode_then_trajectories(handle, generic_handle, code, B, cap):
+    """ldpcb_nms_retest_host (Decoding_model.call in one call): tallies, flags and the 13-row records of the detected
+    failures equal a full-trajectory decode of the batch; a too-small record buffer reports the true count."""
+    y, cw = _edge_frames(code, B, 41)
+    truth = _lib.pack_bits(cw)
+    full = nms_gpu(handle, y, traj=True)
+    want_idx = np.flatnonzero(full["syndrome_nz"])
+    for h in (handle, generic_handle):
+        bits, syn = np.empty((B, 4), np.uint32), np.empty(B, np.uint8)
+        cnt = np.zeros(16, np.uint64)
+        fidx, traj, nf = np.empty(cap, np.int32), np.empty((cap, 13, 128), np.float32), np.zeros(1, np.int64)
+        h.call("ldpcb_nms_retest_host", y, B, 12, ALPHA, 1.0, 1.0, truth, bits, syn, cnt, cap, fidx, traj, nf)
+        n = int(nf[0])
+        assert n == len(want_idx)
+        k = min(n, cap)
+        assert np.array_equal(fidx[:k], want_idx[:k])
+        assert np.array_equal(traj[:k].view(np.uint32), full["traj"][want_idx[:k]].view(np.uint32))
+        assert np.array_equal(_lib.unpack_bits(bits), full["hard"]) and np.array_equal(syn.astype(bool), full["syndrome_nz"])
+        wrong = (full["hard"] != cw).any(1)
+        assert int(cnt[0]) == B and int(cnt[1]) == int(wrong.sum()) and int(cnt[2]) == int((full["hard"] != cw).sum())
+        assert int(cnt[3]) == n and int(cnt[4]) == int((wrong & ~full["syndrome_nz"]).sum()) and int(cnt[9]) == int(cnt[1])
