@@ -45,7 +45,15 @@ def sigma_of(ebn0_db: float, k: int = 64, n: int = 128) -> np.float32:
 
 
 def _u01(x: np.ndarray) -> np.ndarray:
+    """23 random bits + 1/2 (the Box-Muller angle)."""
     return ((x >> np.uint32(9)).astype(np.float64) + 0.5) * 2.0 ** -23
+
+
+def _u01_32(x: np.ndarray) -> np.ndarray:
+    """The Box-Muller radius uniform from all 32 bits, defined in fp32 exactly as csrc/philox.cuh u01_32 computes it:
+    fl32(fl32(float(x) + 0.5) * 2^-32), clamped to the largest float below 1 (tail out to 6.76 sigma)."""
+    u = (x.astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -32)
+    return np.minimum(u, np.float32(0.99999994)).astype(np.float64)
 
 
 def gen_frames(seed: int, first_frame: int, B: int, ebn0_db: float, G: np.ndarray):
@@ -66,10 +74,10 @@ def gen_frames(seed: int, first_frame: int, B: int, ebn0_db: float, G: np.ndarra
     blk = np.arange(32, dtype=np.uint32)
     ctr = np.stack([np.repeat(flo, 32), np.repeat(fhi, 32), np.tile(blk, B), np.zeros(B * 32, np.uint32)], axis=-1)
     x = philox4x32_10(ctr, key)  # [B*32,4]
-    u = _u01(x)
+    u, ur = _u01(x), _u01_32(x)
     z = np.empty((B * 32, 4), dtype=np.float64)
     for a, b in ((0, 1), (2, 3)):
-        r = np.sqrt(-2.0 * np.log(u[:, a]))
+        r = np.sqrt(-2.0 * np.log(ur[:, a]))
         z[:, a] = r * np.cos(2.0 * np.pi * u[:, b])
         z[:, b] = r * np.sin(2.0 * np.pi * u[:, b])
     z = z.reshape(B, n)

@@ -193,6 +193,48 @@ class _PinnedBlock:
                 pass
 
 
+class _PinnedPool:
+    """Recycles pinned blocks by size class (powers of two from 64 KiB): cudaMallocHost costs ~0.3 ms per call, more than a
+    1000-frame decode, so the drop-in entry points that return fresh arrays per call take their result buffers from here.
+    A block goes back to the pool when the last array viewing it is collected; the pool keeps at most `limit` bytes."""
+
+    def __init__(self, limit: int = 1 << 30):
+        self.free, self.held, self.limit = {}, 0, limit
+
+    def take(self, nbytes: int):
+        size = 1 << max(16, (max(nbytes, 1) - 1).bit_length())
+        lst = self.free.get(size)
+        if lst:
+            self.held -= size
+            return _PooledBlock(self, lst.pop(), size)
+        return _PooledBlock(self, _PinnedBlock(load(), size), size)
+
+    def give(self, raw, size: int):
+        if self.held + size <= self.limit:
+            self.free.setdefault(size, []).append(raw)
+            self.held += size
+
+
+class _PooledBlock:
+    def __init__(self, pool, raw, size):
+        self._pool, self._raw, self._size = pool, raw, size
+        self.__array_interface__ = raw.__array_interface__
+
+    def __del__(self):
+        try:
+            self._pool.give(self._raw, self._size)
+        except Exception:
+            pass
+
+
+_POOL = _PinnedPool()
+
+
+def pinned_pool_empty(shape, dtype) -> np.ndarray:
+    """Like pinned_empty, from the recycling pool."""
+    return pinned_empty(shape, dtype, _alloc=_POOL.take)
+
+
 def pinned_empty(shape, dtype, _alloc=None) -> np.ndarray:
     """NumPy array backed by pinned host memory (ldpcb_host_alloc); the memory is released when the array AND
     every view derived from it have been collected.  `_alloc` (tests) substitutes the block allocator."""

@@ -37,6 +37,8 @@ struct __align__(16) Osd3Warp {
 
 constexpr int O3_NONE = 64;  // pass without a third position
 constexpr int O3_INF = 0x7fffffff;
+constexpr int O3_PEN = 1 << 20;   // x 512 = 2^29 added to the score of an element outside the triangle i < j < kl
+constexpr int O3_BIG = 1 << 29;
 // candidate ids: pass << 8 | mi << 6 | nj << 3 | e << 1 ... kept simple: fields below
 __device__ __forceinline__ int o3_id(int pass, int mi, int nj, int e) { return (pass << 7) | (mi << 5) | (nj << 2) | e; }
 constexpr int O3_ID_SINGLE = 1 << 20, O3_ID_EMPTY = 1 << 21;
@@ -61,6 +63,15 @@ __global__ void __launch_bounds__(OSD_THREADS, 4) osd3_kernel(OsdArgs a, const u
     const int g = lane >> 2, t = lane & 3;
     const int vb = g - 2 * t;  // i - j of element 0 of a tile whose row and column blocks start at the same index
     OsdTally tally;
+    // high-plane accumulator initialisers of the tiles on the diagonal: element e = (row g + 8*(e>>1), column 2t + (e&1)) of a
+    // tile whose column block starts dlt = 0 or 8 positions right of its row block is a pair with i >= j iff vb + 8rs - cs >= dlt
+    int pen_d0[4], pen_d8[4];
+    const int pen_none[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        pen_d0[e] = (vb + 8 * (e >> 1) - (e & 1) >= 0) ? -O3_PEN : 0;
+        pen_d8[e] = (vb + 8 * (e >> 1) - (e & 1) >= 8) ? -O3_PEN : 0;
+    }
     const int64_t gw = (int64_t)blockIdx.x * OSD_FPB + warp, nw = (int64_t)gridDim.x * OSD_FPB;
 
     for (int64_t f = gw; f < nframes; f += nw) {
@@ -100,6 +111,7 @@ __global__ void __launch_bounds__(OSD_THREADS, 4) osd3_kernel(OsdArgs a, const u
             for (int q = 0; q < 4; ++q) wr[p][q] = wqw[16 * p + 8 * (q >> 1) + 4 * (q & 1) + t];
 
         int s[3] = {O3_INF, O3_INF, O3_INF}, sid[3] = {0, 0, 0};
+        int gate = O3_INF;  // running warp minimum + OSD_WIN
         const int b32 = F.base32;
         // ---- passes: no third position (pairs, singles, the empty TEP), then k = 2..63 ------------------------
 #pragma unroll 1
@@ -108,6 +120,7 @@ __global__ void __launch_bounds__(OSD_THREADS, 4) osd3_kernel(OsdArgs a, const u
             const unsigned long long dk = pass == O3_NONE ? d0 : d0 ^ F.prow[pass];
             const int bk = b32 + (pass == O3_NONE ? 0 : F.qd32[pass]);
             __syncwarp();  // the previous pass is done with R
+            if (pass != O3_NONE && lane == 0) W.C[pass] = O3_BIG;  // j < kl: passes run downwards, every j > kl is already out
             {
                 const int r0 = bk + F.qd32[lane] + wpop_shfl(tb, dk ^ P.myprow[0]);
                 W.R[lane] = r0;
@@ -121,6 +134,7 @@ __global__ void __launch_bounds__(OSD_THREADS, 4) osd3_kernel(OsdArgs a, const u
                     o3_track(s, sid, r1, O3_ID_SINGLE | (lane + 32));
                     const int ez = bk + wpop_shfl(tb, dk);  // the empty TEP (shuffles are warp-wide: every lane computes it)
                     if (lane == 0) o3_track(s, sid, ez, O3_ID_EMPTY);
+                    gate = __reduce_min_sync(0xffffffffu, s[0]) + OSD_WIN;
                 }
             }
             const uint4 md = make_uint4(mask4((unsigned)dk, 4 * t), mask4((unsigned)dk, 4 * t + 16),
@@ -145,33 +159,38 @@ __global__ void __launch_bounds__(OSD_THREADS, 4) osd3_kernel(OsdArgs a, const u
                             afr[kk][p][2 * hh + 1] = wr[p][2 * kk + hh] & x1[2 * kk + hh];
                         }
                 const int rr0 = W.R[i0], rr1 = W.R[i0 + 8];
-#pragma unroll 1
-                for (int nj = 2 * mi; nj < n_nj; ++nj) {
+                // One 16x8 tile: four IMMAs, scores, gate.  `pen` initialises the high-plane accumulators: -O3_PEN on the
+                // elements with i >= j of the two tiles that touch the diagonal (their score comes out 2^29 too large and
+                // never passes the gate), 0 elsewhere -- the triangle costs no instruction.  Columns j >= kl carry the
+                // same penalty in C (set once per pass, see above).
+                auto tile = [&](int nj, const int (&pen)[4]) {
                     const uint4 bf = W.bfrag[nj][lane];
                     const unsigned b0[2] = {bf.x, bf.y}, b1[2] = {bf.z, bf.w};
-                    int acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-                    imma_u8(acc[0], afr[0][0], b0);
-                    imma_u8(acc[1], afr[0][1], b0);
-                    imma_u8(acc[0], afr[1][0], b1);
-                    imma_u8(acc[1], afr[1][1], b1);
+                    int acc0[4] = {0, 0, 0, 0}, acc1[4] = {pen[0], pen[1], pen[2], pen[3]};
+                    imma_u8(acc0, afr[0][0], b0);
+                    imma_u8(acc1, afr[0][1], b0);
+                    imma_u8(acc0, afr[1][0], b1);
+                    imma_u8(acc1, afr[1][1], b1);
                     const int2 cc = *reinterpret_cast<const int2*>(W.C + 8 * nj + 2 * t);
+                    const int rc[4] = {rr0 + cc.x, rr0 + cc.y, rr1 + cc.x, rr1 + cc.y};
                     int p4[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) p4[e] = ((e >> 1) ? rr1 : rr0) + ((e & 1) ? cc.y : cc.x) - 2 * acc[0][e] - 512 * acc[1][e];
-                    const int dlt = 8 * nj - 16 * mi;
-                    if (dlt < 16 || 8 * nj + 8 > kl) {  // the tile touches the diagonal i = j or the edge j = kl (warp-uniform)
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int rs = e >> 1, cs = e & 1;
-                            if (vb + 8 * rs - cs >= dlt || 8 * nj + 2 * t + cs >= kl) p4[e] = O3_INF;
-                        }
-                    }
+                    for (int e = 0; e < 4; ++e) p4[e] = rc[e] - 2 * acc0[e] - 512 * acc1[e];
                     const int m4 = min(min(p4[0], p4[1]), min(p4[2], p4[3]));
-                    if (m4 < s[2]) {  // rare after the first tiles
+                    // warp-uniform gate: only scores within the truncation window of the running warp minimum can matter
+                    if (__any_sync(0xffffffffu, m4 <= gate)) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) o3_track(s, sid, p4[e], o3_id(pass, mi, nj, e));
+                        for (int e = 0; e < 4; ++e)
+                            if (p4[e] <= gate) o3_track(s, sid, p4[e], o3_id(pass, mi, nj, e));
+                        const int wm = __reduce_min_sync(0xffffffffu, s[0]);
+                        gate = wm > O3_INF - OSD_WIN ? O3_INF : wm + OSD_WIN;
                     }
-                }
+                };
+                int nj = 2 * mi;
+                if (nj < n_nj) tile(nj, pen_d0);
+                if (nj + 1 < n_nj) tile(nj + 1, pen_d8);
+#pragma unroll 2
+                for (nj += 2; nj < n_nj; ++nj) tile(nj, pen_none);
             }
         }
         // ---- candidates inside the truncation window, exact scores ---------------------------------------------------
