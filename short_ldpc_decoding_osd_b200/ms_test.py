@@ -139,7 +139,10 @@ class Decoding_model:
         cap = self._fail_cap if getattr(self, "_fail_cap", 0) else max(64, B // 2)
         while True:
             fidx = np.empty(cap, np.int32)
-            traj = _lib.pinned_pool_empty((cap, rows, 128), np.float32)  # pinned: the 13-row records are most of the traffic
+            # pinned (recycled) memory for the 13-row records, most of the traffic of a call; very large batches take
+            # pageable memory: pinning hundreds of MB per call costs more than it saves
+            big = cap * rows * 512 > (64 << 20)
+            traj = np.empty((cap, rows, 128), np.float32) if big else _lib.pinned_pool_empty((cap, rows, 128), np.float32)
             nf = np.zeros(1, np.int64)
             cnt[:] = 0
             h.call("ldpcb_nms_retest_host", y, B, L.num_iterations, alpha, w_vc, w_marg, truth, bits, syn, cnt, cap, fidx, traj, nf)
