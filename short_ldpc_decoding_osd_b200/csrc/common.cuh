@@ -89,6 +89,8 @@ struct ldpcb_handle {
     std::map<cudaStream_t, ldpcb::Workspace> fb_ws;      // osd3.cu: frames left to the exact sweep, one list per caller stream
     std::map<cudaStream_t, ldpcb::Workspace> stream_ws;  // scratch of the device-pointer calls, one per caller stream
     int occ[ldpcb::OCC_SLOTS] = {};       // resident CTAs per SM of each kernel variant on THIS handle's device (0 = not queried)
+    int qc_minb = 2;                      // nms_qc.cu register budget: 2 CTAs of 8 warps per SM at 110 registers (default: measured
+                                          // faster, 5.61 vs 5.73 ms per 2^21 frames), or 3 at 80 (env LDPCB_QC_MINB=3, A/B timing)
     bool qc_ccsds = false;                // H is the CCSDS (128,64) matrix nms_qc.cu is specialised to
     bool pb_consts_ready = false;         // __constant__ tables of osd_pb.cu uploaded to this device
     char* pb_list = nullptr;       // PB-OSD order 3: TEP lists of the resident warps
@@ -222,7 +224,25 @@ struct FsParams {
     int order;
     int32_t* num_teps;
     uint8_t* stop_kind;  // 0: order-0 accepted, 1: tau_e stop inside a sweep, 2: skip rule, 3: all orders swept
+    // order 3 in three launches (launch_osd_fs3): a frame that reaches the weight-3 class is not swept here but appended,
+    // with the decision so far, to a list that the tensor-core sweep of osd3.cu works off
+    int defer3 = 0;
+    int32_t* d3_list = nullptr;    // original rows
+    int32_t* d3_count = nullptr;
+    long long* d3_wdmin = nullptr; // [list position]
+    int32_t* d3_opt = nullptr;
+    int32_t* d3_num = nullptr;
 };
+struct Fs3Args {
+    const long long* wdmin;   // [list position] exact score of the decision after classes 0..2
+    const int32_t* opt;       // its TEP index (FS enumeration)
+    const int32_t* num;       // TEPs visited so far
+    int he, hs;               // eligible iff |D| < he (= tau_psc - 3); stop iff |D| < hs (= ceil(tau_e) - 3)
+    int32_t* num_teps;        // outputs by original row (may be NULL)
+    uint8_t* stop_kind;
+};
+int launch_osd3_fs(ldpcb_handle* h, const OsdArgs& a, const Fs3Args& fs, int32_t* fb_list, int32_t* fb_count, cudaStream_t st);
+int launch_osd_fs3(ldpcb_handle* h, const OsdArgs& a, const FsParams& fp, cudaStream_t st);  // FS policy, order_limit 3
 int launch_osd_fs(ldpcb_handle* h, const OsdArgs& a, const FsParams& fp, cudaStream_t st);
 
 // PB-OSD policy parameters (PB_OSD/pb_testing.py:44-52,100-149)

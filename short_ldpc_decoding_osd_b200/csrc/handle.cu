@@ -378,6 +378,7 @@ int ldpcb_create(ldpcb_t** out, const uint8_t* H_host, const uint8_t* G_host, in
     for (int i = 0; i < k * n; ++i) h->G[i] = G_host[i] & 1;
     if ((st = build_code_tables(h)) != LDPCB_OK) return fail(st);
     if ((st = build_tep_tables(h)) != LDPCB_OK) return fail(st);
+    if (const char* e = getenv("LDPCB_QC_MINB")) h->qc_minb = atoi(e) == 3 ? 3 : 2;
     h->qc_ccsds = nms_qc_matches_code(h->H) && !getenv("LDPCB_NMS_GENERIC");  // env: force the table-driven kernel (tests, A/B timing)
     if ((st = check_cuda(h, cudaMalloc(&h->one_block_dev, 2 * sizeof(int32_t)), "cudaMalloc")) != LDPCB_OK) return fail(st);
     if ((st = check_cuda(h, cudaMalloc(&h->pb_queue, 256), "cudaMalloc")) != LDPCB_OK) return fail(st);

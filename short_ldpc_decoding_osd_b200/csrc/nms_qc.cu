@@ -101,8 +101,9 @@ __device__ __forceinline__ unsigned rot16u(unsigned v, int src) { return __shfl_
 // FUSE: tallies against truth_bits, append of the frames with a non-zero syndrome to (fail_idx, fail_count) and, when
 //       the frames are generated here (GEN), their channel LLRs + transmitted codewords to fail_llr / fail_truth;
 // GEN:  generate the frame in the prologue (Philox, same floats as gen_frames_kernel) instead of loading it
-template <bool TRAJ, bool FIR, bool FUSE, bool GEN>
-__global__ void __launch_bounds__(QC_THREADS, 2) nms_qc_kernel(NmsArgs a, NmsFuse z) {
+// MINB: resident CTAs per SM the register allocation is held to (2: 110 registers, 3: 80 registers, no spills either way)
+template <bool TRAJ, bool FIR, bool FUSE, bool GEN, int MINB>
+__global__ void __launch_bounds__(QC_THREADS, MINB) nms_qc_kernel(NmsArgs a, NmsFuse z) {
     using namespace qc;
     __shared__ unsigned long long sh_cnt[LDPCB_NUM_COUNTERS];
     __shared__ __align__(16) float sh_gen[GEN ? QC_WARPS * 2 * N : 4];
@@ -357,9 +358,9 @@ __global__ void __launch_bounds__(QC_THREADS, 2) nms_qc_kernel(NmsArgs a, NmsFus
     }
 }
 
-template <bool TRAJ, bool FIR, bool FUSE, bool GEN>
-static int launch_qc_variant(ldpcb_handle* h, const NmsArgs& a, const NmsFuse& z, cudaStream_t st) {
-    auto kern = nms_qc_kernel<TRAJ, FIR, FUSE, GEN>;
+template <bool TRAJ, bool FIR, bool FUSE, bool GEN, int MINB>
+static int launch_qc_minb(ldpcb_handle* h, const NmsArgs& a, const NmsFuse& z, cudaStream_t st) {
+    auto kern = nms_qc_kernel<TRAJ, FIR, FUSE, GEN, MINB>;
     int& occ = h->occ[OCC_NMS_QC + (FUSE ? (GEN ? 4 : 3) : FIR ? 2 : TRAJ ? 1 : 0)];
     if (occ == 0) {
         LDPCB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, QC_THREADS, 0));
@@ -373,6 +374,12 @@ static int launch_qc_variant(ldpcb_handle* h, const NmsArgs& a, const NmsFuse& z
     kern<<<grid, QC_THREADS, 0, st>>>(a, z);
     LDPCB_LAUNCH_CHECK(h, "nms_qc_kernel");
     return LDPCB_OK;
+}
+
+template <bool TRAJ, bool FIR, bool FUSE, bool GEN>
+static int launch_qc_variant(ldpcb_handle* h, const NmsArgs& a, const NmsFuse& z, cudaStream_t st) {
+    if (h->qc_minb == 2) return launch_qc_minb<TRAJ, FIR, FUSE, GEN, 2>(h, a, z, st);
+    return launch_qc_minb<TRAJ, FIR, FUSE, GEN, 3>(h, a, z, st);
 }
 
 bool nms_qc_applies(const ldpcb_handle* h, const NmsArgs& a) {

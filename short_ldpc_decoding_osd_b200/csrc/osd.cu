@@ -30,6 +30,7 @@
 //   5c. block minima (DL path), FS policy and the near-tie fallback: exact 64-bit scores through byte LUTs
 //   6. the TEPs within the truncation window of the minimum are re-scored exactly; lexicographic
 //      (score, index) minimum = first minimum in enumeration order (tf.argmin)
+#include <cmath>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -375,6 +376,7 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_fs_kernel(OsdArgs a, FsParams
                     const long long qv = G.qd[63 - j];
                     bnd += qv < 0 ? -qv : qv;
                     if (!(bnd + shift_q < w_dmin)) { kind = 2; break; }
+                    if (fp.defer3 && j == 2) { kind = 4; break; }  // the weight-3 class goes to the tensor-core sweep (osd3.cu)
                     const int r0 = cls_start[j + 1], r1 = cls_start[j + 2];
                     // The class is swept in chunks of FS_CHUNK TEPs: the sequential loop of the reference stops at the first
                     // TEP closer than tau_e, on average after ~600 (order 2) / ~3000 (order 3) of the 2016 / 41664 TEPs of
@@ -469,6 +471,13 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_fs_kernel(OsdArgs a, FsParams
                 if (a.score_exp) a.score_exp[f] = P.E;
                 if (fp.num_teps) fp.num_teps[orow] = S.fs_num[warp];
                 if (fp.stop_kind) fp.stop_kind[orow] = (uint8_t)S.fs_kind[warp];
+                if (S.fs_kind[warp] == 4) {
+                    const int p = atomicAdd(fp.d3_count, 1);
+                    fp.d3_list[p] = (int32_t)row;
+                    fp.d3_wdmin[p] = S.fs_score[warp];
+                    fp.d3_opt[p] = S.fs_opt[warp];
+                    fp.d3_num[p] = S.fs_num[warp];
+                }
             }
             if (a.perm) {
 #pragma unroll
@@ -495,6 +504,48 @@ int launch_osd_fs(ldpcb_handle* h, const OsdArgs& a, const FsParams& fp, cudaStr
     osd_fs_kernel<<<grid, OSD_THREADS, smem, st>>>(a, fp, h->gcol_dev);
     LDPCB_LAUNCH_CHECK(h, "osd_fs_kernel");
     return LDPCB_OK;
+}
+
+// FS policy at order_limit 3 (the reference's default, FS_OSD/globalmap.py:44) in three launches:
+//   1. osd_fs_kernel, classes 0..2; a frame that reaches class 3 is appended, with its decision so far, to a list
+//   2. osd3_kernel<FS> sweeps class 3 of those frames on the tensor cores (scores + Hamming distances)
+//   3. osd_fs_kernel again, full policy, on the few frames step 2 could not decide (a tau_e stop inside class 3)
+// About 7 % of the NMS failures at 2.5 dB reach class 3 and nearly all of them sweep it completely: 41,664 TEPs through the
+// 64-bit byte LUT was 70 % of the order-3 time.
+int launch_osd_fs3(ldpcb_handle* h, const OsdArgs& a, const FsParams& fp, cudaStream_t st) {
+    if (a.B == 0) return LDPCB_OK;
+    const size_t n = (size_t)a.B;
+    const size_t need = 256 + n * (4 + 4 + 8 + 4 + 4) + 1024;
+    Workspace& w = h->fb_ws[st];
+    if (w.cap < need) {
+        if (w.buf) { LDPCB_CUDA(h, cudaDeviceSynchronize()); LDPCB_CUDA(h, cudaFree(w.buf)); w.buf = nullptr; w.cap = 0; }
+        LDPCB_CUDA(h, cudaMalloc(&w.buf, need + need / 4));
+        w.cap = need + need / 4;
+    }
+    int32_t* counts = reinterpret_cast<int32_t*>(w.buf);            // [0]: deferred, [32]: undecided
+    long long* wdmin = reinterpret_cast<long long*>(w.buf + 256);
+    int32_t* d3_list = reinterpret_cast<int32_t*>(w.buf + 256 + n * 8);
+    int32_t* l3_list = d3_list + n;
+    int32_t* opt = l3_list + n;
+    int32_t* num = opt + n;
+    LDPCB_CUDA(h, cudaMemsetAsync(counts, 0, 256, st));
+    FsParams f1 = fp;
+    f1.defer3 = 1; f1.d3_list = d3_list; f1.d3_count = counts; f1.d3_wdmin = wdmin; f1.d3_opt = opt; f1.d3_num = num;
+    int s = launch_osd_fs(h, a, f1, st);
+    if (s != LDPCB_OK) return s;
+    const int64_t bound = a.B < 32768 ? a.B : 32768;  // grid bound of the follow-up launches: they stride over device-side counts
+    OsdArgs a2 = a;
+    a2.idx = d3_list; a2.count = counts; a2.B = bound;
+    a2.score_exp = nullptr; a2.perm = nullptr; a2.redG = nullptr;  // written by launch 1 for every frame
+    Fs3Args f2;
+    f2.wdmin = wdmin; f2.opt = opt; f2.num = num;
+    f2.he = fp.tau_psc - 3;
+    f2.hs = (int)ceilf(fp.tau_e) - 3;
+    f2.num_teps = fp.num_teps; f2.stop_kind = fp.stop_kind;
+    if ((s = launch_osd3_fs(h, a2, f2, l3_list, counts + 32, st)) != LDPCB_OK) return s;
+    OsdArgs a3 = a2;
+    a3.idx = l3_list; a3.count = counts + 32;
+    return launch_osd_fs(h, a3, fp, st);
 }
 
 template <int MAXW, bool BLOCKS, bool SOLO = false>
@@ -608,5 +659,7 @@ extern "C" int ldpcb_osd_fs_decode(ldpcb_t* h, const float* llr_dev, int64_t B, 
     FsParams fp;
     fp.tau_e = tau_e; fp.tau_psc = tau_psc; fp.beta_shift = beta_shift; fp.order = order_limit;
     fp.num_teps = num_teps_dev; fp.stop_kind = stop_kind_dev;
+    a.pair_index = t.pair_dev; a.triple_index = t.triple_dev;
+    if (order_limit == 3 && !getenv("LDPCB_FS3_EXACT")) return launch_osd_fs3(h, a, fp, (cudaStream_t)stream);
     return launch_osd_fs(h, a, fp, (cudaStream_t)stream);
 }

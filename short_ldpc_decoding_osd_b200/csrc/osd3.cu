@@ -33,6 +33,8 @@ struct __align__(16) Osd3Warp {
     uint4 maskp[64][4];   // [row i][t]: byte masks (0x00 / 0xFF) of the same four nibbles of P'_i
     int C[64];
     int R[64];
+    int HC[64];           // FS: |P'_j| (Hamming weights for the tau_e / tau_psc tests), 2^20 for j >= kl
+    int HR[64];           // FS, per pass: |d_k ^ P'_i|
 };
 
 constexpr int O3_NONE = 64;  // pass without a third position
@@ -51,8 +53,13 @@ __device__ __forceinline__ void o3_track(int (&s)[3], int (&id)[3], int p, int p
     }
 }
 
-__global__ void __launch_bounds__(OSD_THREADS, 4) osd3_kernel(OsdArgs a, const uint64_t* __restrict__ gcol, const uint16_t* __restrict__ triple_index,
-                                                              int32_t* fb_list, int32_t* fb_count) {
+// FS = the weight-3 class of the FS policy (FS_OSD/fs_testing.py:137-152) for the frames osd_fs_kernel deferred: only the
+// 62 passes with a third position run; a third, unit-weight IMMA plane gives every triple's Hamming distance to the hard
+// decision (|u ^ P_j| = |u| + |P_j| - 2 sum u.P_j), TEPs at distance >= tau_psc are not eligible, and a frame in which any
+// triple is closer than tau_e (the sequential loop would stop there) or whose window overflows goes to the exact kernel.
+template <bool FS>
+__global__ void __launch_bounds__(OSD_THREADS, FS ? 3 : 4) osd3_kernel(OsdArgs a, const uint64_t* __restrict__ gcol, const uint16_t* __restrict__ triple_index,
+                                                                       int32_t* fb_list, int32_t* fb_count, Fs3Args fs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     Osd3Warp& W = reinterpret_cast<Osd3Warp*>(smem_raw)[warp];
@@ -87,6 +94,7 @@ __global__ void __launch_bounds__(OSD_THREADS, 4) osd3_kernel(OsdArgs a, const u
             const unsigned wa = F.w32[lane], wb = F.w32[lane + 32];
             W.C[lane] = F.qd32[lane] + wpop_shfl(tb, P.myprow[0]);
             W.C[lane + 32] = F.qd32[lane + 32] + wpop_shfl(tb, P.myprow[1]);
+            if (FS) { W.HC[lane] = __popcll(P.myprow[0]); W.HC[lane + 32] = __popcll(P.myprow[1]); }
             __syncwarp();  // every lane is done with w32 as words: the byte planes go to ys
             unsigned char* wq = reinterpret_cast<unsigned char*>(F.ys);  // [plane][LRB position]
             wq[lane] = (unsigned char)(wa & 0xffu); wq[lane + 32] = (unsigned char)(wb & 0xffu);
@@ -114,16 +122,21 @@ __global__ void __launch_bounds__(OSD_THREADS, 4) osd3_kernel(OsdArgs a, const u
         int gate = O3_INF;  // running warp minimum + OSD_WIN
         const int b32 = F.base32;
         // ---- passes: no third position (pairs, singles, the empty TEP), then k = 2..63 ------------------------
+        bool any_stop = false;
 #pragma unroll 1
-        for (int pass = O3_NONE; pass != 1; pass = (pass == O3_NONE ? 63 : pass - 1)) {
+        for (int pass = FS ? 63 : O3_NONE; pass != 1; pass = (pass == O3_NONE ? 63 : pass - 1)) {
             const int kl = pass;  // pairs i < j < kl
             const unsigned long long dk = pass == O3_NONE ? d0 : d0 ^ F.prow[pass];
             const int bk = b32 + (pass == O3_NONE ? 0 : F.qd32[pass]);
             __syncwarp();  // the previous pass is done with R
-            if (pass != O3_NONE && lane == 0) W.C[pass] = O3_BIG;  // j < kl: passes run downwards, every j > kl is already out
+            if (pass != O3_NONE && lane == 0) {  // j < kl: passes run downwards, every j > kl is already out
+                W.C[pass] = O3_BIG;
+                if (FS) W.HC[pass] = O3_PEN;
+            }
             {
                 const int r0 = bk + F.qd32[lane] + wpop_shfl(tb, dk ^ P.myprow[0]);
                 W.R[lane] = r0;
+                if (FS) { W.HR[lane] = __popcll(dk ^ P.myprow[0]); W.HR[lane + 32] = __popcll(dk ^ P.myprow[1]); }
                 int r1 = O3_INF;
                 if (kl > 32) {  // warp-uniform
                     r1 = bk + F.qd32[lane + 32] + wpop_shfl(tb, dk ^ P.myprow[1]);
@@ -158,6 +171,17 @@ __global__ void __launch_bounds__(OSD_THREADS, 4) osd3_kernel(OsdArgs a, const u
                             afr[kk][p][2 * hh] = wr[p][2 * kk + hh] & x0[2 * kk + hh];
                             afr[kk][p][2 * hh + 1] = wr[p][2 * kk + hh] & x1[2 * kk + hh];
                         }
+                unsigned afh[2][4];  // FS: unit-weight plane (the mask bits as bytes)
+                if (FS) {
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            afh[kk][2 * hh] = x0[2 * kk + hh] & 0x01010101u;
+                            afh[kk][2 * hh + 1] = x1[2 * kk + hh] & 0x01010101u;
+                        }
+                }
+                const int hr0 = FS ? W.HR[i0] : 0, hr1 = FS ? W.HR[i0 + 8] : 0;
                 const int rr0 = W.R[i0], rr1 = W.R[i0 + 8];
                 // One 16x8 tile: four IMMAs, scores, gate.  `pen` initialises the high-plane accumulators: -O3_PEN on the
                 // elements with i >= j of the two tiles that touch the diagonal (their score comes out 2^29 too large and
@@ -176,6 +200,19 @@ __global__ void __launch_bounds__(OSD_THREADS, 4) osd3_kernel(OsdArgs a, const u
                     int p4[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) p4[e] = rc[e] - 2 * acc0[e] - 512 * acc1[e];
+                    if (FS) {
+                        int acch[4] = {pen[0], pen[1], pen[2], pen[3]};  // excluded elements come out 2^21 too far
+                        imma_u8(acch, afh[0], b0);
+                        imma_u8(acch, afh[1], b1);
+                        const int2 hc = *reinterpret_cast<const int2*>(W.HC + 8 * nj + 2 * t);
+                        const int hrc[4] = {hr0 + hc.x, hr0 + hc.y, hr1 + hc.x, hr1 + hc.y};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int hd = hrc[e] - 2 * acch[e];
+                            any_stop |= hd < fs.hs;
+                            if (hd >= fs.he) p4[e] = O3_INF;
+                        }
+                    }
                     const int m4 = min(min(p4[0], p4[1]), min(p4[2], p4[3]));
                     // warp-uniform gate: only scores within the truncation window of the running warp minimum can matter
                     if (__any_sync(0xffffffffu, m4 <= gate)) {
@@ -195,8 +232,9 @@ __global__ void __launch_bounds__(OSD_THREADS, 4) osd3_kernel(OsdArgs a, const u
         }
         // ---- candidates inside the truncation window, exact scores ---------------------------------------------------
         int m = __reduce_min_sync(0xffffffffu, s[0]);
-        const int lim = m + OSD_WIN;
-        const bool fallback = __any_sync(0xffffffffu, s[2] <= lim);  // a thread may have dropped a fourth candidate
+        const int lim = m > O3_INF - OSD_WIN ? O3_INF - 1 : m + OSD_WIN;  // m = INF: FS class without an eligible TEP
+        // a thread may have dropped a fourth candidate; FS: the sequential loop would have stopped inside this class
+        const bool fallback = __any_sync(0xffffffffu, s[2] <= lim) || (FS && __any_sync(0xffffffffu, any_stop));
         long long best_s = 0x7fffffffffffffffll;
         int best_i = 0x7fffffff;
         unsigned best_pos = 0xffffffffu;
@@ -244,6 +282,19 @@ __global__ void __launch_bounds__(OSD_THREADS, 4) osd3_kernel(OsdArgs a, const u
             }
         } else if (lane == 0) {
             fb_list[atomicAdd(fb_count, 1)] = (int32_t)row;
+        }
+        if (FS && !fallback) {
+            // the decision so far (classes 0..2) stands unless the class holds a strictly smaller eligible score (:148-152)
+            const long long w0 = fs.wdmin[f];
+            if (!(best_s < w0)) {
+                best_s = w0;
+                best_i = fs.opt[f];
+                best_pos = __ldg(a.teps + best_i);
+            }
+            if (lane == 0) {
+                if (fs.num_teps) fs.num_teps[row] = fs.num[f] + 41664;
+                if (fs.stop_kind) fs.stop_kind[row] = 3;
+            }
         }
         // ---- outputs -----------------------------------------------------------------------------------------------
         if (!fallback) {
@@ -295,8 +346,8 @@ int launch_osd3(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st) {
     const int smem = OSD_FPB * (int)sizeof(Osd3Warp);
     int& occ = h->occ[OCC_OSD3];
     if (occ == 0) {
-        LDPCB_CUDA(h, cudaFuncSetAttribute(osd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        LDPCB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, osd3_kernel, OSD_THREADS, smem));
+        LDPCB_CUDA(h, cudaFuncSetAttribute(osd3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        LDPCB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, osd3_kernel<false>, OSD_THREADS, smem));
         if (occ < 1) occ = 1;
     }
     // the list of frames left to the exact sweep: a buffer of its own per caller stream
@@ -314,7 +365,7 @@ int launch_osd3(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st) {
     int64_t cap = (int64_t)h->sm_count * occ;
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
-    osd3_kernel<<<grid, OSD_THREADS, smem, st>>>(a, h->gcol_dev, triple_index, fb_list, fb_count);
+    osd3_kernel<false><<<grid, OSD_THREADS, smem, st>>>(a, h->gcol_dev, triple_index, fb_list, fb_count, Fs3Args{});
     LDPCB_LAUNCH_CHECK(h, "osd3_kernel");
     // exact sweep of the undecided frames: they are addressed by their ORIGINAL row, results go to the same places
     OsdArgs b = a;
@@ -323,6 +374,25 @@ int launch_osd3(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st) {
     b.pair_index = nullptr;
     b.B = a.B < 4096 ? a.B : 4096;  // grid bound only: the kernel strides over the device-side count
     return launch_osd_generic3(h, b, st);
+}
+
+// The weight-3 class of the FS policy for the frames osd_fs_kernel deferred (a.idx / a.count = that list).  Frames the
+// sweep cannot decide (a tau_e stop inside the class, window overflow) are appended to (fb_list, fb_count).
+int launch_osd3_fs(ldpcb_handle* h, const OsdArgs& a, const Fs3Args& fs, int32_t* fb_list, int32_t* fb_count, cudaStream_t st) {
+    const int smem = OSD_FPB * (int)sizeof(Osd3Warp);
+    int& occ = h->occ[OCC_OSD3 + 1];
+    if (occ == 0) {
+        LDPCB_CUDA(h, cudaFuncSetAttribute(osd3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        LDPCB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, osd3_kernel<true>, OSD_THREADS, smem));
+        if (occ < 1) occ = 1;
+    }
+    int64_t want = (a.B + OSD_FPB - 1) / OSD_FPB;
+    int64_t cap = (int64_t)h->sm_count * occ;
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    osd3_kernel<true><<<grid, OSD_THREADS, smem, st>>>(a, h->gcol_dev, a.triple_index, fb_list, fb_count, fs);
+    LDPCB_LAUNCH_CHECK(h, "osd3_kernel<FS>");
+    return LDPCB_OK;
 }
 
 }  // namespace ldpcb

@@ -145,3 +145,40 @@ def test_order3_tensor_sweep_equals_generic_sweep_on_many_frames(code):
         for u, v, name in zip(out[("tensor", tep_order)], out[("generic", tep_order)], ("codeword", "best_tep", "best_score_q")):
             assert np.array_equal(u, v), (tep_order, name, int((u != v).sum()))
     hq.close()
+
+
+@pytest.mark.parametrize("ebn0,tau_e,tau_psc,beta", [(2.5, 6.5, 30, 6.4), (1.5, 6.5, 30, 6.4), (2.5, 9.0, 26, 12.8), (3.5, 4.0, 34, 3.2)])
+def test_fs_order3_three_launch_path_equals_single_kernel(code, ebn0, tau_e, tau_psc, beta):
+    """FS policy at order_limit 3: classes 0..2 + deferred tensor-core class 3 + exact kernel for the undecided frames
+    (launch_osd_fs3) against the single exact kernel (LDPCB_FS3_EXACT=1): codeword, decision index, visited TEPs, stop kind
+    and exact score of every frame, on NMS failures at several SNRs and threshold settings."""
+    import os
+
+    import torch
+
+    from short_ldpc_decoding_osd_b200 import _lib
+    from tests.gpu_util import empty, sync
+
+    h = _lib.Handle(code.H, code.G, device=0)
+    B = 1 << 18
+    y = empty((B, 128), torch.float32)
+    h.call("ldpcb_gen_frames", 11, 0, B, ebn0, y, None, None)
+    bits, it, syn = empty((B, 4), torch.int32), empty((B,), torch.uint8), empty((B,), torch.uint8)
+    h.call("ldpcb_nms_decode", y, B, 12, ALPHA, 1.0, 1.0, 0, bits, it, syn, None, None)
+    yf = y[syn.bool()][:40000].contiguous()
+    n = yf.shape[0]
+    out = {}
+    for tag in ("three", "exact"):
+        if tag == "exact":
+            os.environ["LDPCB_FS3_EXACT"] = "1"
+        try:
+            cw, bt, nt, sk, bq = empty((n, 4), torch.int32), empty((n,), torch.int32), empty((n,), torch.int32), empty((n,), torch.uint8), empty((n,), torch.int64)
+            h.call("ldpcb_osd_fs_decode", yf, n, 3, tau_e, tau_psc, beta, cw, bt, nt, sk, bq, None, None, None)
+            sync()
+            out[tag] = [x.cpu().numpy() for x in (cw, bt, nt, sk, bq)]
+        finally:
+            os.environ.pop("LDPCB_FS3_EXACT", None)
+    for name, u, v in zip(("codeword", "best_tep", "num_teps", "stop_kind", "best_score_q"), out["three"], out["exact"]):
+        assert np.array_equal(u, v), (name, int((u != v).sum()), n)
+    assert (out["exact"][3] == 3).sum() > 0  # some frames do sweep all three classes
+    h.close()
