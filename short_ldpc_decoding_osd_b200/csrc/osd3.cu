@@ -187,7 +187,8 @@ __global__ void __launch_bounds__(OSD_THREADS, FS ? 3 : 4) osd3_kernel(OsdArgs a
                 // elements with i >= j of the two tiles that touch the diagonal (their score comes out 2^29 too large and
                 // never passes the gate), 0 elsewhere -- the triangle costs no instruction.  Columns j >= kl carry the
                 // same penalty in C (set once per pass, see above).
-                auto tile = [&](int nj, const int (&pen)[4]) {
+                // scores of one tile (p4) from its four (FS: six) IMMAs
+                auto tile_scores = [&](int nj, const int (&pen)[4], int (&p4)[4]) {
                     const uint4 bf = W.bfrag[nj][lane];
                     const unsigned b0[2] = {bf.x, bf.y}, b1[2] = {bf.z, bf.w};
                     int acc0[4] = {0, 0, 0, 0}, acc1[4] = {pen[0], pen[1], pen[2], pen[3]};
@@ -197,7 +198,6 @@ __global__ void __launch_bounds__(OSD_THREADS, FS ? 3 : 4) osd3_kernel(OsdArgs a
                     imma_u8(acc1, afr[1][1], b1);
                     const int2 cc = *reinterpret_cast<const int2*>(W.C + 8 * nj + 2 * t);
                     const int rc[4] = {rr0 + cc.x, rr0 + cc.y, rr1 + cc.x, rr1 + cc.y};
-                    int p4[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) p4[e] = rc[e] - 2 * acc0[e] - 512 * acc1[e];
                     if (FS) {
@@ -213,21 +213,47 @@ __global__ void __launch_bounds__(OSD_THREADS, FS ? 3 : 4) osd3_kernel(OsdArgs a
                             if (hd >= fs.he) p4[e] = O3_INF;
                         }
                     }
-                    const int m4 = min(min(p4[0], p4[1]), min(p4[2], p4[3]));
-                    // warp-uniform gate: only scores within the truncation window of the running warp minimum can matter
-                    if (__any_sync(0xffffffffu, m4 <= gate)) {
+                };
+                // warp-uniform gate: only scores within the truncation window of the running warp minimum can matter
+                auto offer = [&](int nj, const int (&p4)[4]) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (p4[e] <= gate) o3_track(s, sid, p4[e], o3_id(pass, mi, nj, e));
-                        const int wm = __reduce_min_sync(0xffffffffu, s[0]);
-                        gate = wm > O3_INF - OSD_WIN ? O3_INF : wm + OSD_WIN;
+                    for (int e = 0; e < 4; ++e)
+                        if (p4[e] <= gate) o3_track(s, sid, p4[e], o3_id(pass, mi, nj, e));
+                };
+                auto regate = [&]() {
+                    const int wm = __reduce_min_sync(0xffffffffu, s[0]);
+                    gate = wm > O3_INF - OSD_WIN ? O3_INF : wm + OSD_WIN;
+                };
+                // One 16x8 tile.  `pen` initialises the high-plane accumulators: -O3_PEN on the elements with i >= j of
+                // the two tiles that touch the diagonal (their score comes out 2^29 too large and never passes the gate),
+                // 0 elsewhere -- the triangle costs no instruction.  Columns j >= kl carry the same penalty in C.
+                auto tile = [&](int nj, const int (&pen)[4]) {
+                    int p4[4];
+                    tile_scores(nj, pen, p4);
+                    const int m4 = min(min(p4[0], p4[1]), min(p4[2], p4[3]));
+                    if (__any_sync(0xffffffffu, m4 <= gate)) {
+                        offer(nj, p4);
+                        regate();
+                    }
+                };
+                // two interior tiles at once: eight independent IMMAs in flight, one gate test for both
+                auto tile2 = [&](int nj) {
+                    int pa[4], pb[4];
+                    tile_scores(nj, pen_none, pa);
+                    tile_scores(nj + 1, pen_none, pb);
+                    const int m8 = min(min(min(pa[0], pa[1]), min(pa[2], pa[3])), min(min(pb[0], pb[1]), min(pb[2], pb[3])));
+                    if (__any_sync(0xffffffffu, m8 <= gate)) {
+                        offer(nj, pa);
+                        offer(nj + 1, pb);
+                        regate();
                     }
                 };
                 int nj = 2 * mi;
                 if (nj < n_nj) tile(nj, pen_d0);
                 if (nj + 1 < n_nj) tile(nj + 1, pen_d8);
-#pragma unroll 2
-                for (nj += 2; nj < n_nj; ++nj) tile(nj, pen_none);
+#pragma unroll 1
+                for (nj += 2; nj + 1 < n_nj; nj += 2) tile2(nj);
+                if (nj < n_nj) tile(nj, pen_none);
             }
         }
         // ---- candidates inside the truncation window, exact scores ---------------------------------------------------
