@@ -3,7 +3,7 @@
     python scripts/make_traffic.py gpurun_out/prof.ncu-rep gpurun_out/prof_stamp.json
 
 The JSON holds, per decoder kernel, DRAM bytes and executed warp instructions PER FRAME (ncu `dram__bytes_read.sum +
-dram__bytes_write.sum` and `sm__inst_executed.sum` divided by the frames of the launch) and is stamped with the hash
+dram__bytes_write.sum` and `smsp__inst_executed.sum` divided by the frames of the launch) and is stamped with the hash
 of the kernel sources the capture ran (short_ldpc_decoding_osd_b200.build._stamp(), written next to the report by
 profile_case.py on the GPU box).  bench.py refuses the file when the stamp differs from the library it is timing.
 """
@@ -27,7 +27,7 @@ def num(r, name, scale_unit=True):
 
 
 out = {"source": f"ncu --set full --clock-control none on scripts/profile_case.py ({meta['frames']} frames per launch), report {os.path.basename(rep)}; "
-                 "dram__bytes_read.sum + dram__bytes_write.sum and sm__inst_executed.sum divided by the frames of the launch",
+                 "dram__bytes_read.sum + dram__bytes_write.sum and smsp__inst_executed.sum divided by the frames of the launch",
        "build_stamp": meta["build_stamp"], "frames": meta["frames"]}
 keys = {"nms": "nms_kernel", "osd_pair": "osd_kernel", "osd_kernel": "osd_kernel_order1", "osd3": "osd_kernel_order3"}
 for r in rows[2:]:
@@ -38,7 +38,7 @@ for r in rows[2:]:
     frames = meta["frames_of"].get(key, meta["frames"])
     rd, wr = num(r, "dram__bytes_read.sum"), num(r, "dram__bytes_write.sum")
     out[key] = {"kernel": name[:100], "frames": frames, "dram_bytes_per_frame": round((rd + wr) / frames, 1), "read_MB": round(rd / 1e6, 3),
-                "write_MB": round(wr / 1e6, 3), "warp_instr_per_frame": round(num(r, "sm__inst_executed.sum", False) / frames, 1),
+                "write_MB": round(wr / 1e6, 3), "warp_instr_per_frame": round(num(r, "smsp__inst_executed.sum", False) / frames, 1),
                 "time_us_under_ncu": round(num(r, "gpu__time_duration.sum", False) * {"ns": 1e-3, "us": 1, "ms": 1e3}.get(units[ix["gpu__time_duration.sum"]], 1), 1)}
 dst = os.path.join(ROOT, "profiles", "r02_traffic.json")
 json.dump(out, open(dst, "w"), indent=1)

@@ -13,7 +13,7 @@ def val(m):
     try: return float(r[ix[m]].replace(",", ""))
     except Exception: return None
 print(f"## {r[ix['Kernel Name']]}  grid {r[ix['launch__grid_size']]} block {r[ix['launch__block_size']]}  ({int(frames)} frames in this launch)")
-M = [("gpu__time_duration.sum", "time under ncu"), ("sm__inst_executed.sum", "warp instructions"), ("sm__inst_executed.avg.per_cycle_elapsed", "IPC per SM (of 4)"),
+M = [("gpu__time_duration.sum", "time under ncu"), ("smsp__inst_executed.sum", "warp instructions"), ("sm__inst_executed.avg.per_cycle_elapsed", "IPC per SM (of 4)"),
      ("smsp__issue_active.avg.pct", "issue slots busy %"), ("sm__warps_active.avg.per_cycle_active", "warps active per SM"), ("launch__registers_per_thread", "registers"),
      ("launch__occupancy_limit_registers", "CTAs/SM by registers"), ("launch__occupancy_limit_shared_mem", "CTAs/SM by shared memory"),
      ("dram__bytes_read.sum", "DRAM read"), ("dram__bytes_write.sum", "DRAM written"), ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput %"),

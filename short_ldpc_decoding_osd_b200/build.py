@@ -44,7 +44,9 @@ def _stamp() -> str:
             with open(p, "rb") as f:
                 h.update(name.encode())
                 h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    # flags without the include paths: the hash must be the same wherever the tree is checked out (the GPU box runs a copy
+    # under another root, and profiles/r02_traffic.json carries the stamp of the library it was measured on)
+    h.update(" ".join(f for f in NVCC_FLAGS if f not in (INCLUDE, CSRC)).encode())
     return h.hexdigest()
 
 

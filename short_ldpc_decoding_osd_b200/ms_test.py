@@ -136,7 +136,8 @@ class Decoding_model:
         bits = np.empty((B, 4), np.uint32)
         syn = np.empty(B, np.uint8)
         cnt = np.zeros(_lib.NUM_COUNTERS, np.uint64)
-        cap = self._fail_cap if getattr(self, "_fail_cap", 0) else max(64, B // 2)
+        # room for the records: half the batch, or what the last call's failure rate suggests (low SNR)
+        cap = max(64, int(B * max(0.5, min(1.0, 1.2 * getattr(self, "_fail_rate", 0.0)))))
         while True:
             fidx = np.empty(cap, np.int32)
             # pinned (recycled) memory for the 13-row records, most of the traffic of a call; very large batches take
@@ -150,7 +151,7 @@ class Decoding_model:
             if n <= cap:
                 break
             cap = n  # more failures than the buffer held (low SNR): once more with room for all of them
-        self._fail_cap = max(cap, 64)
+        self._fail_rate = n / max(B, 1)
         fer = float(cnt[1]) / B
         ber = float(cnt[2]) / (B * lab.shape[1])
         undetected = int(cnt[4])
