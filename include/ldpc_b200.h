@@ -82,7 +82,10 @@ enum {
      * (DL path: ordered_statistics_decoding.py:182-189 scores against the channel LLR while the MRB
      * hard decisions come from the ordering metric).  Default: from order_llr
      * (FS_OSD/convention_osd.py:54-60; PB_OSD/convention_osd.py:54-61). */
-    LDPCB_OSD_DISC_HARD_FROM_SCORE = 2
+    LDPCB_OSD_DISC_HARD_FROM_SCORE = 2,
+    /* ldpcb_osd_block_minima only: largest TEP weight in the caller's list (1..4) as a hint, flags |= w << 4; 0 = unknown
+     * (treated as 4).  The sweep touches `w` generator rows per TEP instead of 4. */
+    LDPCB_OSD_MAXW_SHIFT = 4
 };
 
 /* Indices into the uint64 counter block filled by ldpcb_tally / ldpcb_decode_* . */

@@ -18,6 +18,7 @@ NUM_COUNTERS = 16
 TEP_CONV, TEP_FS = 0, 1
 OSD_TIES_HIGH_INDEX_FIRST = 1
 OSD_DISC_HARD_FROM_SCORE = 2
+OSD_MAXW_SHIFT = 4
 
 COUNTER_NAMES = [
     "frames", "nms_frame_err", "nms_bit_err", "nms_detected", "nms_undetected", "nms_iters",

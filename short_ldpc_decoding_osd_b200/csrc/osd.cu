@@ -624,7 +624,9 @@ extern "C" int ldpcb_osd_block_minima(ldpcb_t* h, const float* order_llr_dev, co
                                       int32_t* score_exp_dev, const uint32_t* truth_bits_dev,
                                       int64_t* truth_score_q_dev, uint8_t* perm_dev, void* stream) {
     LDPCB_ENTER(h);
-    if (B < 0 || n_teps < 0 || n_blocks < 1 || (flags & ~3))
+    const int maxw_hint = (flags >> LDPCB_OSD_MAXW_SHIFT) & 7;
+    flags &= ~(7 << LDPCB_OSD_MAXW_SHIFT);
+    if (B < 0 || n_teps < 0 || n_blocks < 1 || (flags & ~3) || maxw_hint > 4)
         return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_block_minima: B=%lld n_teps=%d n_blocks=%d flags=%d out of range", (long long)B, n_teps, n_blocks, flags);
     if (B == 0) return LDPCB_OK;
     int st = check_llr(h, "ldpcb_osd_block_minima", order_llr_dev, score_llr_dev);
@@ -633,7 +635,7 @@ extern "C" int ldpcb_osd_block_minima(ldpcb_t* h, const float* order_llr_dev, co
         return set_error(h, LDPCB_ERR_ARG, "ldpcb_osd_block_minima: NULL teps, block_start or block_min_q");
     OsdArgs a = {};
     a.order_llr = order_llr_dev; a.score_llr = score_llr_dev; a.B = B;
-    a.teps = teps_dev; a.n_teps = n_teps; a.maxw = 4; a.flags = flags;
+    a.teps = teps_dev; a.n_teps = n_teps; a.maxw = maxw_hint ? maxw_hint : 4; a.flags = flags;
     a.block_start = block_start_dev; a.n_blocks = n_blocks;
     a.block_min_q = block_min_q_dev; a.block_arg = block_arg_dev; a.score_exp = score_exp_dev;
     a.truth_bits = truth_bits_dev; a.truth_score_q = truth_score_q_dev; a.perm = perm_dev;

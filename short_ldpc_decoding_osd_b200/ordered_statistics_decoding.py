@@ -121,8 +121,9 @@ class osd:
         ts = torch.empty((B,), dtype=torch.int64, device=dev)
         pm = torch.empty((B, 128), dtype=torch.uint8, device=dev)
         truth = t(_lib.pack_bits(np.asarray(labels).reshape(B, 128)).view(np.int32))
+        maxw = min(4, max(1, max(int(np.asarray(b).sum(axis=1).max()) for b in teps_list)))  # hint: rows touched per TEP
         h.call("ldpcb_osd_block_minima", t(order_metric), t(channel), B, t(packed.view(np.int32)), len(packed), t(starts), nb,
-               FLAGS_DL, bm, None, ex, truth, ts, pm, None)
+               FLAGS_DL | (maxw << _lib.OSD_MAXW_SHIFT), bm, None, ex, truth, ts, pm, None)
         torch.cuda.synchronize()
         return bm.cpu().numpy(), ts.cpu().numpy(), ex.cpu().numpy(), pm.cpu().numpy()
 

@@ -152,6 +152,7 @@ def run_point_dl(handle, ebn0_db: float, total_frames: int, tep_info, taps, bias
     stream = torch.cuda.current_stream(dev).cuda_stream
     teps_list, acc = tep_info
     packed = torch.from_numpy(np.concatenate([pack_dl_teps(b) for b in teps_list]).view(np.int32)).to(dev)
+    flags_dl = FLAGS_DL | (min(4, max(1, max(int(np.asarray(b).sum(axis=1).max()) for b in teps_list))) << _lib.OSD_MAXW_SHIFT)
     starts = torch.from_numpy(np.asarray(acc, dtype=np.int32)).to(dev)
     nb = len(teps_list)
     taps = np.ascontiguousarray(taps, dtype=np.float32)
@@ -190,7 +191,7 @@ def run_point_dl(handle, ebn0_db: float, total_frames: int, tep_info, taps, bias
                 handle.call("ldpcb_gather_rows", metric_all, idx, cnt, nf, 128, metric, stream)
                 handle.call("ldpcb_gather_rows", truth.view(torch.float32), idx, cnt, nf, 4, truth_f.view(torch.float32), stream)
                 bm, ex, ts = e((nf, nb), torch.int64), e((nf,), torch.int32), e((nf,), torch.int64)
-                handle.call("ldpcb_osd_block_minima", metric, llr_f, nf, packed, int(packed.numel()), starts, nb, FLAGS_DL, bm, None, ex,
+                handle.call("ldpcb_osd_block_minima", metric, llr_f, nf, packed, int(packed.numel()), starts, nb, flags_dl, bm, None, ex,
                             truth_f, ts, None, stream)
                 handle.call("ldpcb_dl_window_policy", bm, ex, ts, nf, nb, int(win_width), W1, W2, float(soft_margin), acc_np, None, None, None,
                             dl, stream)
