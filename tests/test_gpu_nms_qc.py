@@ -194,3 +194,31 @@ def test_retest_host_equals_decode_then_trajectories(handle, generic_handle, cod
         wrong = (full["hard"] != cw).any(1)
         assert int(cnt[0]) == B and int(cnt[1]) == int(wrong.sum()) and int(cnt[2]) == int((full["hard"] != cw).sum())
         assert int(cnt[3]) == n and int(cnt[4]) == int((wrong & ~full["syndrome_nz"]).sum()) and int(cnt[9]) == int(cnt[1])
+
+
+def test_handles_of_two_devices_in_one_thread(code):
+    """every entry point makes its handle's device current (and restores the caller's), so handles of several
+    devices can be interleaved from one thread.  Needs two GPUs; skipped on a one-GPU box."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    B = 5000
+    y, cw = _edge_frames(code, B, 51)
+    truth = _lib.pack_bits(cw).view(np.int32)
+    hs = [_lib.Handle(code.H, code.G, device=d) for d in (0, 1)]
+    assert torch.cuda.current_device() == 0  # ldpcb_create restored the caller's device
+    bufs = []
+    for d in (0, 1):
+        dev_ = f"cuda:{d}"
+        bufs.append((torch.from_numpy(y).to(dev_), torch.from_numpy(truth).to(dev_), torch.empty((B, 4), dtype=torch.int32, device=dev_),
+                     torch.zeros(16, dtype=torch.int64, device=dev_)))
+    for rep in range(3):  # alternate devices without ever calling cudaSetDevice ourselves
+        for h, (yd, tr, bits, cnt) in zip(hs, bufs):
+            h.call("ldpcb_decode", yd, B, 12, ALPHA, 1.0, 1.0, 0, 2, 0, bits, None, None, tr, cnt, None)
+            assert torch.cuda.current_device() == 0
+    for d in (0, 1):
+        torch.cuda.synchronize(d)
+    r0, r1 = bufs[0][2].cpu().numpy(), bufs[1][2].cpu().numpy()
+    assert np.array_equal(r0, r1) and np.array_equal(bufs[0][3].cpu().numpy(), bufs[1][3].cpu().numpy())
+    assert int(bufs[0][3][0].item()) == 3 * B
+    for h in hs:
+        h.close()
