@@ -97,11 +97,12 @@ def test_qc_fir_variant_equals_generic(handle, generic_handle, code):
         assert np.array_equal(u.view(np.uint8), v.view(np.uint8))
 
 
-@pytest.mark.parametrize("order,B", [(2, 20001), (1, 4099), (0, 513), (3, 300), (-1, 1000)])
+@pytest.mark.parametrize("order,B", [(2, 20001), (1, 4099), (0, 513), (3, 300), (-1, 1000), (2, 1), (2, 2), (3, 3), (1, 7)])
 def test_fused_decode_equals_unfused_pipeline(handle, generic_handle, code, order, B):
     """ldpcb_decode on the fused path (NMS + tallies + failure list in one kernel, OSD + tallies in the other) gives
     the same decisions, flags, TEP choices and all 16 counters as the 7-launch pipeline."""
-    y, cw = _edge_frames(code, B, 21)
+    y, cw = _edge_frames(code, max(B, 8), 21)
+    y, cw = np.ascontiguousarray(y[:B]), np.ascontiguousarray(cw[:B])
     truth = dev(_lib.pack_bits(cw).view(np.int32))
     res = []
     for h in (handle, generic_handle):
