@@ -563,8 +563,8 @@ def measure_configs(h, torch, llr, truth, fails_llr, nfail, sp, stream, ebn0, fi
         rng = np.random.default_rng(3)
         taps = (np.full(13, 1 / 13) + 0.03 * rng.normal(size=13)).astype(np.float32)
         net = nn_net.Predict_outlier_light(5, W1=np.eye(6, dtype=np.float32), W2=np.array([[0, -0.5], [0, 0.5], [0, 0], [0, 0], [0, 0], [0, 0.15]], np.float32))
-        n = 1 << 20
-        simulate.run_point_dl(h, ebn0, 1 << 18, tep_info, taps, 0.05, net.W1, net.W2, seed=1)
+        n = 1 << 22
+        simulate.run_point_dl(h, ebn0, 1 << 22, tep_info, taps, 0.05, net.W1, net.W2, seed=1)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         simulate.run_point_dl(h, ebn0, n, tep_info, taps, 0.05, net.W1, net.W2, seed=2)

@@ -13,7 +13,7 @@
 // (mod 16): one __shfl_sync(.., width 16) moves the 16 messages of a class of BOTH frames of the warp, and the 14
 // classes with delta = 0 (rho, sigma were chosen to maximise them) need no exchange at all.  Per iteration and frame
 // that is 18 shuffle operations for 512 messages in each direction, against 52 shared-memory operations in nms.cu,
-// and about 150 instead of 236 issued instructions.
+// and 176 instead of 236 issued instructions (2252 instead of 2833 per frame, ncu).
 //
 // Variable totals are summed in ascending check order like tf.reduce_sum over the check axis (oracle/nms_oracle.py):
 // block rows ascending; the two checks a variable of a diagonal block has in ONE block row are ordered by a per-lane

@@ -137,7 +137,7 @@ def run_point(handle, ebn0_db: float, total_frames: int, seed: int = 0, osd_orde
 
 
 def run_point_dl(handle, ebn0_db: float, total_frames: int, tep_info, taps, bias: float, W1, W2, soft_margin: float = 0.9,
-                 win_width: int = 5, seed: int = 0, iters: int = 12, alpha: float = 0.66943514, chunk: int = 1 << 20,
+                 win_width: int = 5, seed: int = 0, iters: int = 12, alpha: float = 0.66943514, chunk: int = 1 << 22,
                  rank: int = 0, world: int = 1):
     """One Eb/N0 point of the DL scheme (BASELINE config 4), everything on the device: generate -> NMS with the DIA FIR
     (ordering metric) fused in -> detected failures -> block minima along the decoding path, scored against the
