@@ -50,19 +50,26 @@ def _stamp() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    os.makedirs(BUILD_DIR, exist_ok=True)
-    stamp_file = os.path.join(BUILD_DIR, "stamp")
+BOUNDS_LIB_PATH = os.path.join(HERE, "libldpc_b200_bounds.so")
+
+
+def build(force: bool = False, verbose: bool = False, bounds: bool = False) -> str:
+    """bounds=True: the same sources with -DLDPCB_BOUNDS (device-side asserts on every data-dependent index) into
+    libldpc_b200_bounds.so; load it with LDPCB_B200_LIB=<path> (tests run scripts/sanitize_case.py against it)."""
+    lib_path = BOUNDS_LIB_PATH if bounds else LIB_PATH
+    build_dir = BUILD_DIR + ("_bounds" if bounds else "")
+    os.makedirs(build_dir, exist_ok=True)
+    stamp_file = os.path.join(build_dir, "stamp")
     stamp = _stamp()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp_file):
+    if not force and os.path.exists(lib_path) and os.path.exists(stamp_file):
         with open(stamp_file) as f:
             if f.read().strip() == stamp:
-                return LIB_PATH
+                return lib_path
     nvcc = _nvcc()
-    extra = ["-Xptxas", "-v"] if verbose else []
+    extra = (["-Xptxas", "-v"] if verbose else []) + (["-DLDPCB_BOUNDS"] if bounds else [])
 
     def compile_one(src: str) -> str:
-        obj = os.path.join(BUILD_DIR, src.replace(".cu", ".o"))
+        obj = os.path.join(build_dir, src.replace(".cu", ".o"))
         cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
@@ -73,15 +80,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(6, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", lib_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     with open(stamp_file, "w") as f:
         f.write(stamp)
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv, bounds="--bounds" in sys.argv)
     print(path)

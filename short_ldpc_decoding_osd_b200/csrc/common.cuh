@@ -135,6 +135,17 @@ struct DeviceGuard {
         if (_st != LDPCB_OK) return _st;                            \
     } while (0)
 
+// Device-side bounds checks of every data-dependent index (list appends, inverse-table lookups, decoded candidate
+// positions).  Compiled in only by `python -m short_ldpc_decoding_osd_b200.build --bounds` (a separate
+// libldpc_b200_bounds.so): compute-sanitizer is closed on the GPU pool, so tests/test_gpu_pipeline.py runs
+// scripts/sanitize_case.py -- every kernel once, ragged sizes -- against that build; a violated check traps the kernel.
+#ifdef LDPCB_BOUNDS
+#include <cassert>
+#define LDPCB_ASSERT(cond) assert(cond)
+#else
+#define LDPCB_ASSERT(cond) ((void)0)
+#endif
+
 #define LDPCB_LAUNCH_CHECK(h, name)                                 \
     do {                                                            \
         (h)->launches++;                                            \

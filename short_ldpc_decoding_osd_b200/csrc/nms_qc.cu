@@ -322,6 +322,7 @@ __global__ void __launch_bounds__(QC_THREADS, MINB) nms_qc_kernel(NmsArgs a, Nms
                 }
                 if (nz && z.fail_count) {
                     pos = atomicAdd(z.fail_count, 1);
+                    LDPCB_ASSERT(pos >= 0 && pos < a.B);
                     if (z.fail_idx) z.fail_idx[pos] = (int32_t)f;
                     if (GEN && z.fail_truth) {
 #pragma unroll

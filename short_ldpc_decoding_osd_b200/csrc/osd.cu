@@ -473,6 +473,7 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_fs_kernel(OsdArgs a, FsParams
                 if (fp.stop_kind) fp.stop_kind[orow] = (uint8_t)S.fs_kind[warp];
                 if (S.fs_kind[warp] == 4) {
                     const int p = atomicAdd(fp.d3_count, 1);
+                    LDPCB_ASSERT(p >= 0 && p < nframes);
                     fp.d3_list[p] = (int32_t)row;
                     fp.d3_wdmin[p] = S.fs_score[warp];
                     fp.d3_opt[p] = S.fs_opt[warp];

@@ -285,6 +285,7 @@ __global__ void __launch_bounds__(OSD_THREADS, FS ? 3 : 4) osd3_kernel(OsdArgs a
                     } else {
                         const int pass = cid >> 7, mi = (cid >> 5) & 3, nj = (cid >> 2) & 7, e = cid & 3;
                         const int i = 16 * mi + (src >> 2) + 8 * (e >> 1), j = 8 * nj + 2 * (src & 3) + (e & 1);
+                        LDPCB_ASSERT(i >= 0 && i < j && j < K && (pass == O3_NONE || (pass >= 2 && pass < K && j < pass)));
                         if (pass == O3_NONE) {
                             pos = 0xffff0000u | ((unsigned)j << 8) | (unsigned)i;
                             ci = (int)a.pair_index[i * K + j];
@@ -294,6 +295,7 @@ __global__ void __launch_bounds__(OSD_THREADS, FS ? 3 : 4) osd3_kernel(OsdArgs a
                             ci = (int)triple_index[k * (k - 1) * (k - 2) / 6 + j * (j - 1) / 2 + i];
                         }
                     }
+                    LDPCB_ASSERT(ci >= 0 && ci < a.n_teps && __ldg(a.teps + ci) == pos);  // the inverse tables and the enumeration agree
                     unsigned long long D = d0;
                     long long sm = F.base;
 #pragma unroll
@@ -307,7 +309,9 @@ __global__ void __launch_bounds__(OSD_THREADS, FS ? 3 : 4) osd3_kernel(OsdArgs a
                 }
             }
         } else if (lane == 0) {
-            fb_list[atomicAdd(fb_count, 1)] = (int32_t)row;
+            const int fp_ = atomicAdd(fb_count, 1);
+            LDPCB_ASSERT(fp_ >= 0 && fp_ < a.B + 64);
+            fb_list[fp_] = (int32_t)row;
         }
         if (FS && !fallback) {
             // the decision so far (classes 0..2) stands unless the class holds a strictly smaller eligible score (:148-152)

@@ -153,7 +153,9 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_pair_kernel(OsdArgs a, con
                     } else {
                         pi = K * K + (cd == PW_CODE_EMPTY ? K : src + 32 * (cd - PW_CODE_SINGLE));
                     }
+                    LDPCB_ASSERT(pi >= 0 && pi < OSD_PAIR_TABLE);
                     const int ci = (int)a.pair_index[pi];
+                    LDPCB_ASSERT(ci >= 0 && ci < a.n_teps);
                     long long sc = 0;
                     if (exact) {
                         const unsigned tw = __ldg(a.teps + ci);

@@ -211,6 +211,7 @@ __device__ __forceinline__ Prep prepare_frame(const OsdArgs& a, FrameSm& F, cons
     unsigned long long myprow[2] = {0ull, 0ull};
     unsigned long long hd_lrb = 0ull, ho_mrb = 0ull, d0 = 0ull;
     int E = 0;
+    LDPCB_ASSERT(row >= 0 && f >= 0);
     // ---- load ---------------------------------------------------------------------------
     const float4 v = reinterpret_cast<const float4*>(a.order_llr + row * N)[lane];
     reinterpret_cast<float4*>(F.yo)[lane] = v;

@@ -263,3 +263,22 @@ def test_dl_device_pipeline_equals_module_chain(handle, code):
     s, f, w, c = osd.sliding_osd(net, rows, nn(squashed), labels0, tep_info)
     assert (out["dl_success"], out["dl_failure"], out["windows_sum"], out["complexity_sum"]) == (s, f, w, c)
     assert s + f == t.nms_detected and out["fer_final"] == (f + und) / B
+
+
+def test_every_kernel_under_the_bounds_check_build():
+    """compute-sanitizer is closed on the GPU pool.  Instead: the library built with -DLDPCB_BOUNDS (device-side asserts on
+    every data-dependent index: failure-list appends, inverse TEP tables, decoded candidate positions) runs
+    scripts/sanitize_case.py -- every kernel at ragged sizes, quantised inputs for the exact fallbacks -- in a child
+    process; a violated assert traps the kernel and the child exits non-zero."""
+    import os
+    import subprocess
+    import sys
+
+    from short_ldpc_decoding_osd_b200 import build
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = build.build(bounds=True)
+    env = dict(os.environ, LDPCB_B200_LIB=lib)
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "sanitize_case.py")], capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
+    assert "sanitize case done" in r.stdout
