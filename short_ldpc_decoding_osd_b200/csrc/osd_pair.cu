@@ -21,6 +21,9 @@ struct __align__(16) PairSmem {
 };
 
 constexpr int PW_CODE_SINGLE = 80, PW_CODE_EMPTY = 82;  // codes 0..79: (tile << 2) | element
+constexpr int PW_PEN = 16384;  // x 65536 = 2^30 on the packed score of an excluded element (real packed scores stay below 2^30)
+// packed scores (S << 7 | code) that can still be inside the truncation window when the minimum is m
+__device__ __forceinline__ int pw_gate(int m) { return m > 0x7fffffff - ((OSD_WIN + 1) << 7) ? 0x7fffffff : ((((m >> 7) + OSD_WIN) << 7) | 127); }
 
 __global__ void __launch_bounds__(OSD_THREADS, 6) osd_pair_kernel(OsdArgs a, const uint64_t* __restrict__ gcol) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -32,6 +35,15 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_pair_kernel(OsdArgs a, con
     const bool disc_from_score = (a.flags & LDPCB_OSD_DISC_HARD_FROM_SCORE) != 0;
     const int g = lane >> 2, t = lane & 3;
     OsdTally tally;
+    // element e of a tile = (row g + 8*(e>>1), column 2t + (e&1)); in a tile whose column block starts dlt = 0 or 8 positions
+    // right of its row block it is a pair with i >= j iff (g - 2t) + 8*(e>>1) - (e&1) >= dlt
+    int pen_d0[4], pen_d8[4];
+    const int pen_none[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        pen_d0[e] = ((g - 2 * t) + 8 * (e >> 1) - (e & 1) >= 0) ? -PW_PEN : 0;
+        pen_d8[e] = ((g - 2 * t) + 8 * (e >> 1) - (e & 1) >= 8) ? -PW_PEN : 0;
+    }
 
     for (int64_t f0 = (int64_t)blockIdx.x * OSD_FPB; f0 < nframes; f0 += (int64_t)gridDim.x * OSD_FPB) {
         const int64_t f = f0 + warp;
@@ -79,8 +91,8 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_pair_kernel(OsdArgs a, con
                 for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) wr[p][kk][hh] = wqw[16 * p + 8 * kk + 4 * hh + t];
-            const int vb = g - 2 * t;  // i - j of element 0 in a tile on the diagonal
             int code = 0;
+            int gate = pw_gate(__reduce_min_sync(0xffffffffu, s0));  // the singles and the empty TEP are tracked already
 #pragma unroll 1
             for (int mi = 0; mi < 4; ++mi) {
                 // masked weights of rows 16mi+g and +8
@@ -103,8 +115,11 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_pair_kernel(OsdArgs a, con
                         }
                     }
                 }
-#pragma unroll 1
-                for (int nj = 2 * mi; nj < 8; ++nj, code += 4) {
+                // One 16x8 tile.  The triangle i < j costs nothing: the two tiles of a row block that touch the diagonal start
+                // their high-plane accumulators at -PW_PEN on the elements with i >= j (the packed score comes out 2^30 too
+                // large).  A thread's two smallest scores are tracked behind a warp-uniform gate (running warp minimum +
+                // truncation window): every score that can still be a candidate at the end passes it.
+                auto tile = [&](int nj, const int (&pen)[4]) {
                     const unsigned long long cj = F.prow[8 * nj + g];
                     unsigned bfr[2][2];
 #pragma unroll
@@ -112,23 +127,32 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_pair_kernel(OsdArgs a, con
 #pragma unroll
                         for (int hh = 0; hh < 2; ++hh)
                             bfr[kk][hh] = spread4(kk ? (unsigned)(cj >> 32) : (unsigned)cj, 4 * t + 16 * hh);
-                    int acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+                    int acc[2][4] = {{0, 0, 0, 0}, {pen[0], pen[1], pen[2], pen[3]}};
 #pragma unroll
                     for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
                         for (int p = 0; p < 2; ++p) imma_u8(acc[p], afr[kk][p], bfr[kk]);
                     const int2 cc = *reinterpret_cast<const int2*>(RC + 64 + 8 * nj + 2 * t);
-                    const int dlt = 8 * nj - 16 * mi;
-                    const bool diag = dlt < 16;  // the tile straddles the diagonal (warp-uniform)
+                    int p4[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int rs = e >> 1, cs = e & 1;
-                        const int rc = (rs ? rr1 : rr0) + (cs ? cc.y : cc.x) + (code + e);
-                        int p = rc - 256 * acc[0][e] - 65536 * acc[1][e];  // ((R + C - 2M) << 7) | code
-                        if (diag && vb + 8 * rs - cs >= dlt) p = 0x7fffffff;  // i >= j
-                        track2(s0, s1, p);
+                        const int rc = ((e >> 1) ? rr1 : rr0) + ((e & 1) ? cc.y : cc.x) + (code + e);
+                        p4[e] = rc - 256 * acc[0][e] - 65536 * acc[1][e];  // ((R + C - 2M) << 7) | code
                     }
-                }
+                    const int m4 = min(min(p4[0], p4[1]), min(p4[2], p4[3]));
+                    if (__any_sync(0xffffffffu, m4 <= gate)) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (p4[e] <= gate) track2(s0, s1, p4[e]);
+                        gate = pw_gate(__reduce_min_sync(0xffffffffu, s0));
+                    }
+                    code += 4;
+                };
+                int nj = 2 * mi;
+                tile(nj, pen_d0);
+                tile(nj + 1, pen_d8);
+#pragma unroll 1
+                for (nj += 2; nj < 8; ++nj) tile(nj, pen_none);
             }
             // ---- candidates inside the truncation window, exact scores ----------------------------------------------
             int m = s0;
