@@ -5,6 +5,12 @@ testing_data_labels int64[F,128])`` with the reference's channel model (``:13-51
 codewords, no LLR scaling).  The reference draws from NumPy's unseeded global MT19937 stream; here the frames
 come from the counter-based Philox kernel (ldpcb_gen_frames), so frame f of a run depends only on (seed, f) and
 any shard can be generated on any GPU.  Rayleigh fading (``:21-38``) is out of scope (off in every driver).
+
+``replay_numpy_seed=s`` replays the reference's own noise instead: the frames ``np.random.seed(s)`` followed by the
+reference's ``testing_data_generating`` would produce (legacy MT19937 stream: ``normal(1, sigma, [F, n])`` drawn
+first, then ``randint(0, 2, [F, k])``, ``:40-45``), bit for bit -- the way to hand both decoders identical inputs
+in a parity run.  A sequential MT19937 stream cannot be sharded, so this mode is host NumPy by nature (it is the
+reference's generator, not a decoder path) and is not what the Monte-Carlo harness uses.
 """
 from __future__ import annotations
 
@@ -15,9 +21,20 @@ from . import globalmap as GL
 from .runtime import get_handle
 
 
-def testing_data_generating(code, SNR, max_frame, seed: int = 0, first_frame: int = 0):
+def testing_data_generating(code, SNR, max_frame, seed: int = 0, first_frame: int = 0, replay_numpy_seed=None):
     if GL.map.get("Rayleigh_fading"):
         raise NotImplementedError("Rayleigh fading is not part of the hot path (Main_test.py:34 sets it False)")
+    if replay_numpy_seed is not None:
+        n, k = int(code.check_matrix_column), int(code.k)
+        F = int(max_frame)
+        rs = np.random.RandomState(int(replay_numpy_seed))  # the stream np.random.seed(s) gives the reference
+        sigma = np.sqrt(1.0 / (2 * (float(k) / float(n)) * 10 ** (SNR / 10)))
+        channel = rs.normal(1, sigma, size=(F, n))           # data_generating.py:40 -- drawn before the messages
+        if GL.map.get("ALL_ZEROS_CODEWORD_TESTING"):
+            return channel, np.zeros((F, n), dtype=np.int64)
+        msg = rs.randint(0, 2, size=[F, k], dtype=int)       # :42
+        cw = msg.dot(np.asarray(code.G)) % 2                 # :43
+        return np.where(cw == 0, channel, -channel), cw      # :44-45 (float64, like the reference; its files store float32)
     import torch  # device memory carrier only
 
     h = get_handle(code)

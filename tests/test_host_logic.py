@@ -171,3 +171,22 @@ def test_exported_weights_round_trip(tmp_path):
     q = tmp_path / "path.json"
     q.write_text(json.dumps({"decoding_path": [[0, 0, 0, 0, 0, 0], [1, 0, 0, 0, 0, 0], [0, 1, 0, 0, 0, 0]], "counts": [9, 5, 2]}))
     assert weights.load_decoding_path(str(q))[1] == [1, 0, 0, 0, 0, 0]
+
+
+def test_generator_replays_the_reference_numpy_stream(golden_dir):
+    """north_star: the frame generator "can replay the reference's noise seeds".  With replay_numpy_seed the drop-in
+    returns exactly what np.random.seed(s) + the reference's testing_data_generating return (fixture: the reference's
+    own function run with seed 0, 4000 frames, 2.5 dB -- oracle/ref_runner.py run_gen)."""
+    import os
+
+    from short_ldpc_decoding_osd_b200 import data_generating as DG
+    from short_ldpc_decoding_osd_b200.fill_matrix_info import Code
+
+    g = np.load(os.path.join(golden_dir, "gen_ref_stats.npz"))
+    code = Code()
+    y, lab = DG.testing_data_generating(code, float(g["snr"]), int(g["n"]), replay_numpy_seed=0)
+    assert y.dtype == np.float64 and y.shape == (int(g["n"]), 128)
+    assert np.array_equal(y[:8].astype(np.float32), g["y_head"])
+    assert np.array_equal(lab[:8].astype(np.uint8), g["labels_head"])
+    z = np.where(lab == 0, y, -y) - 1.0
+    assert abs(float(z.std()) - float(g["sigma_hat"])) < 1e-6 and abs(float(lab.mean()) - float(g["ones_frac"])) < 1e-12  # the fixture took its moments on the float32 copy
