@@ -92,6 +92,7 @@ struct ldpcb_handle {
     int qc_minb = 2;                      // nms_qc.cu register budget: 2 CTAs of 8 warps per SM at 110 registers (default: measured
                                           // faster, 5.61 vs 5.73 ms per 2^21 frames), or 3 at 80 (env LDPCB_QC_MINB=3, A/B timing)
     bool qc_ccsds = false;                // H is the CCSDS (128,64) matrix nms_qc.cu is specialised to
+    int occ_pb[3] = {0, 0, 0};            // osd_pb_kernel at 6 / 8 / 10 CTAs per SM
     bool pb_consts_ready = false;         // __constant__ tables of osd_pb.cu uploaded to this device
     char* pb_list = nullptr;       // PB-OSD order 3: TEP lists of the resident warps
     size_t pb_list_cap = 0;        // in list entries

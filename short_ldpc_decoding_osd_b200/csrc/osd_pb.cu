@@ -11,6 +11,8 @@
 // TEP order and weighted distances use the exact integer reliabilities; probabilities are evaluated in fp32 in
 // the order the reference evaluates them (oracle/pb_oracle.py restates it and matches the reference's per-frame
 // S/F, TEP counts and improvement counters on the golden frames); binomial CDFs in fp64.
+#include <cstdlib>
+
 #include "osd_prepare.cuh"
 
 namespace ldpcb {
@@ -44,7 +46,11 @@ __device__ __forceinline__ float mean64_pairwise(const float* v, int lane) {
 
 // The TEP list of each warp is a slice of pp.glist_sum / pp.glist_tep (global memory, L2-resident in practice): shared
 // memory only holds the prepared frame, so 28 warps per SM are resident instead of the 4 a 25 KB list per warp allowed.
-__global__ void __launch_bounds__(OSD_THREADS) osd_pb_kernel(OsdArgs a, PbParams pp, const uint64_t* __restrict__ gcol) {
+// MINB: resident CTAs per SM the register allocation is held to: 6 -> 80 registers, 8 -> 64, 10 -> 48 (60 B spilled).  Measured
+// (scripts/pb_ab.py, order 2 at 3.0 dB, 1e5 failures): 1.455e7 / 1.421e7 / 1.390e7 frames/s -- more resident warps do not help,
+// the 24-warp configuration stays the default (env LDPCB_PB_MINB selects the others for A/B timing).
+template <int MINB>
+__global__ void __launch_bounds__(OSD_THREADS, MINB) osd_pb_kernel(OsdArgs a, PbParams pp, const uint64_t* __restrict__ gcol) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     PbHead& W = reinterpret_cast<PbHead*>(smem_raw)[warp];
@@ -263,6 +269,40 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_pb_kernel(OsdArgs a, PbParams
     }
 }
 
+constexpr int PB_DEFAULT_MINB = 6;
+
+template <int MINB>
+static int launch_pb_minb(ldpcb_handle* h, const OsdArgs& a, const PbParams& pp, bool cap_order3, cudaStream_t st) {
+    // lists in global memory: one slice per resident warp
+    const int smem = OSD_FPB * (int)sizeof(PbHead);
+    int& occ = h->occ_pb[MINB == 6 ? 0 : MINB == 8 ? 1 : 2];
+    if (occ == 0) {
+        LDPCB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, osd_pb_kernel<MINB>, OSD_THREADS, smem));
+        if (occ < 1) occ = 1;
+    }
+    int64_t want = (a.B + OSD_FPB - 1) / OSD_FPB;
+    // order 3: a warp's list slice is 43,776 entries (0.5 MB), 1.9 GB of lists at 24 warps per SM; capping the grid at 16 warps
+    // per SM to keep them smaller measured 3-5 % slower, so the cap is opt-in (env LDPCB_PB_CAP3)
+    int64_t cap = (int64_t)h->sm_count * (pp.order >= 3 && cap_order3 && occ > 4 ? 4 : occ);
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    const size_t per = (size_t)grid * OSD_FPB * pb_glist_cap(pp.order);
+    if (h->pb_list_cap < per) {
+        if (h->pb_list) { LDPCB_CUDA(h, cudaDeviceSynchronize()); LDPCB_CUDA(h, cudaFree(h->pb_list)); h->pb_list = nullptr; h->pb_list_cap = 0; }
+        LDPCB_CUDA(h, cudaMalloc(&h->pb_list, per * (sizeof(long long) + sizeof(unsigned)) + per / 32 * sizeof(long long)));
+        h->pb_list_cap = per;
+    }
+    PbParams q = pp;
+    q.queue = h->pb_queue;
+    LDPCB_CUDA(h, cudaMemsetAsync(h->pb_queue, 0, sizeof(int), st));
+    q.glist_sum = reinterpret_cast<long long*>(h->pb_list);
+    q.glist_bmin = reinterpret_cast<long long*>(h->pb_list + per * sizeof(long long));
+    q.glist_tep = reinterpret_cast<unsigned*>(h->pb_list + per * sizeof(long long) + per / 32 * sizeof(long long));
+    osd_pb_kernel<MINB><<<grid, OSD_THREADS, smem, st>>>(a, q, h->gcol_dev);
+    LDPCB_LAUNCH_CHECK(h, "osd_pb_kernel");
+    return LDPCB_OK;
+}
+
 int launch_osd_pb(ldpcb_handle* h, const OsdArgs& a, const PbParams& pp, cudaStream_t st) {
     if (a.B == 0) return LDPCB_OK;
     if (!h->pb_consts_ready) {
@@ -276,34 +316,12 @@ int launch_osd_pb(ldpcb_handle* h, const OsdArgs& a, const PbParams& pp, cudaStr
         LDPCB_CUDA(h, cudaMemcpyToSymbol(c_binom64, c, sizeof c));
         h->pb_consts_ready = true;
     }
-    {
-        // lists in global memory: one slice per resident warp
-        const int smem = OSD_FPB * (int)sizeof(PbHead);
-        int& occ = h->occ[OCC_OSD_PB];
-        if (occ == 0) {
-            LDPCB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, osd_pb_kernel, OSD_THREADS, smem));
-            if (occ < 1) occ = 1;
-        }
-        int64_t want = (a.B + OSD_FPB - 1) / OSD_FPB;
-        int64_t cap = (int64_t)h->sm_count * (pp.order >= 3 && occ > 4 ? 4 : occ);  // order 3: 16 warps per SM = 1.2 GB of lists
-        int grid = (int)(want < cap ? want : cap);
-        if (grid < 1) grid = 1;
-        const size_t per = (size_t)grid * OSD_FPB * pb_glist_cap(pp.order);
-        if (h->pb_list_cap < per) {
-            if (h->pb_list) { LDPCB_CUDA(h, cudaDeviceSynchronize()); LDPCB_CUDA(h, cudaFree(h->pb_list)); h->pb_list = nullptr; h->pb_list_cap = 0; }
-            LDPCB_CUDA(h, cudaMalloc(&h->pb_list, per * (sizeof(long long) + sizeof(unsigned)) + per / 32 * sizeof(long long)));
-            h->pb_list_cap = per;
-        }
-        PbParams q = pp;
-        q.queue = h->pb_queue;
-        LDPCB_CUDA(h, cudaMemsetAsync(h->pb_queue, 0, sizeof(int), st));
-        q.glist_sum = reinterpret_cast<long long*>(h->pb_list);
-        q.glist_bmin = reinterpret_cast<long long*>(h->pb_list + per * sizeof(long long));
-        q.glist_tep = reinterpret_cast<unsigned*>(h->pb_list + per * sizeof(long long) + per / 32 * sizeof(long long));
-        osd_pb_kernel<<<grid, OSD_THREADS, smem, st>>>(a, q, h->gcol_dev);
-        LDPCB_LAUNCH_CHECK(h, "osd_pb_kernel");
-        return LDPCB_OK;
-    }
+    const char* e = getenv("LDPCB_PB_MINB");  // A/B timing of the register budget
+    const int minb = e ? atoi(e) : PB_DEFAULT_MINB;
+    const bool cap3 = getenv("LDPCB_PB_CAP3") != nullptr;
+    if (minb == 6) return launch_pb_minb<6>(h, a, pp, cap3, st);
+    if (minb == 10) return launch_pb_minb<10>(h, a, pp, cap3, st);
+    return launch_pb_minb<8>(h, a, pp, cap3, st);
 }
 
 }  // namespace ldpcb

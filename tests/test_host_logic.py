@@ -190,3 +190,27 @@ def test_generator_replays_the_reference_numpy_stream(golden_dir):
     assert np.array_equal(lab[:8].astype(np.uint8), g["labels_head"])
     z = np.where(lab == 0, y, -y) - 1.0
     assert abs(float(z.std()) - float(g["sigma_hat"])) < 1e-6 and abs(float(lab.mean()) - float(g["ones_frac"])) < 1e-12  # the fixture took its moments on the float32 copy
+
+
+def test_retest_buffer_row_sequences_behave_like_the_reference_lists():
+    """ms_test._Rows: the (buffer_inputs, buffer_labels) Decoding_model returns are row sequences over one array each;
+    the reference's drivers index, slice, iterate, len() and concatenate them (ldpc_128_testing.py:123-125,
+    ms_test.py:66-70)."""
+    from short_ldpc_decoding_osd_b200 import ms_test as M
+
+    base = np.arange(6 * 128, dtype=np.float32).reshape(6, 128)
+    rows = M._Rows(base)
+    assert len(rows) == 6 and np.array_equal(rows[2], base[2]) and np.array_equal(rows[-1], base[5])
+    assert [r[0] for r in rows] == [float(base[i, 0]) for i in range(6)]
+    assert np.array_equal(np.stack(rows[1:3]), base[1:3]) and np.array_equal(np.asarray(rows), base)
+    lab = np.arange(3 * 128).reshape(3, 128)
+    rep = M._Rows(lab, np.repeat(np.array([2, 0]), 13))          # label of failure i repeated 13 times
+    assert len(rep) == 26 and np.array_equal(rep[0], lab[2]) and np.array_equal(rep[13], lab[0])
+    assert np.array_equal(rep.array(), lab[np.repeat(np.array([2, 0]), 13)])
+    assert len(rows + rep) == 32 and len([1] + rows) == 7        # list concatenation both ways
+    model = M.Decoding_model.__new__(M.Decoding_model)
+    flat_i, flat_l = model.postprocess_failure_cases(([rows, rows], [rep, rep]))
+    assert len(flat_i) == 12 and len(flat_l) == 52 and np.array_equal(flat_i.array()[6:], base)
+    # the reference's list-of-lists form still works
+    flat_i, flat_l = model.postprocess_failure_cases(([[base[0], base[1]]], [[lab[0], lab[1]]]))
+    assert len(flat_i) == 2 and np.array_equal(flat_i[1], base[1])
