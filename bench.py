@@ -532,13 +532,13 @@ def measure_configs(h, torch, llr, truth, fails_llr, nfail, sp, stream, ebn0, fi
         out[f"fs_osd_order{order}_on_nms_failures"] = rate(n, lambda: h.call("ldpcb_osd_fs_decode", fails_llr, n, order, 6.5, 30, 6.4, cw, None, nt, sk, None, None, None, sp))
         out[f"fs_osd_order{order}_on_nms_failures"]["mean_teps"] = float(nt[:n].float().mean().item())
     # PB-OSD: BASELINE config 3 is order 2 at 3.0 dB; order 3 is the reference's default order_limit
-    Bp = min(B, 1 << 19)
+    Bp = min(B, 1 << 20)
     y3, t3, b3, s3, i3 = e((Bp, 128), torch.float32), e((Bp, 4), torch.int32), e((Bp, 4), torch.int32), e((Bp,), torch.uint8), e((Bp,), torch.uint8)
     h.call("ldpcb_gen_frames", 2025, first_frame, Bp, 3.0, y3, t3, sp)
     h.call("ldpcb_nms_decode", y3, Bp, 12, ALPHA, 1.0, 1.0, 0, b3, i3, s3, None, sp)
     f3 = y3[s3.bool()].contiguous()
     st4 = e((max(f3.shape[0], 1), 4), torch.int32)
-    for order, cap in ((2, 1 << 16), (3, 1 << 16)):
+    for order, cap in ((2, 1 << 17), (3, 1 << 16)):
         n = min(f3.shape[0], cap)
         if n:
             out[f"pb_osd_order{order}_ebn0_3.0dB_on_nms_failures"] = rate(n, lambda: h.call("ldpcb_osd_pb_decode", f3, n, order, 3.0, cw, st4, None, None, sp))
