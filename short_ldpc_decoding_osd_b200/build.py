@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB_PATH = os.path.join(HERE, "libldpc_b200.so")
 BUILD_DIR = os.path.join(ROOT, "build", "ldpc_b200")
-SOURCES = ["handle.cu", "nms.cu", "nms_qc.cu", "osd.cu", "osd_pair.cu", "osd3.cu", "osd_pb.cu", "aux.cu", "framegen.cu", "pipeline.cu"]
+SOURCES = ["handle.cu", "nms.cu", "nms_qc.cu", "osd.cu", "osd_pair.cu", "osd3.cu", "osd_blocks.cu", "osd_pb.cu", "aux.cu", "framegen.cu", "pipeline.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -69,7 +69,7 @@ struct Workspace {
 };
 // slots of ldpcb_handle::occ (occupancy is a property of (kernel, device), so it lives in the handle)
 enum { OCC_NMS = 0 /* +0..7: template variants */, OCC_NMS_QC = 8 /* +0..4 */, OCC_OSD = 13 /* +0..8 */, OCC_OSD_FS = 23, OCC_OSD_PAIR = 24,
-       OCC_OSD_PB = 25, OCC_OSD3 = 26, OCC_SLOTS = 32 };
+       OCC_OSD_PB = 25, OCC_OSD3 = 26 /* +0..1 */, OCC_OSD_BLOCKS = 28 /* +0..3 */, OCC_SLOTS = 32 };
 
 }  // namespace ldpcb
 
@@ -226,6 +226,7 @@ struct OsdArgs {
 };
 int launch_osd(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st);
 int launch_osd_pair(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st);
+int launch_osd_blocks(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st);  // block minima: per-block truncated sweep + exact re-scoring (osd_blocks.cu)
 int launch_osd3(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st);      // order 3, full lists: tensor-core sweep of the 62 pair problems (osd3.cu)  // order 2, full lists: warp-local tensor-core pair sweep
 
 // FS-OSD policy parameters (FS_OSD/fs_testing.py:92,129-160)

@@ -573,6 +573,7 @@ int launch_osd_generic3(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st) { re
 int launch_osd(ldpcb_handle* h, const OsdArgs& a, cudaStream_t st) {
     if (a.B == 0) return LDPCB_OK;
     const bool blocks = a.block_start != nullptr;
+    if (blocks && !getenv("LDPCB_BLOCKS_LUT")) return launch_osd_blocks(h, a, st);  // osd_blocks.cu; the variable keeps the byte-LUT sweep below for A/B runs
     switch (a.maxw) {
         case 1:
             if (blocks) return launch_variant<1, true>(h, a, st);

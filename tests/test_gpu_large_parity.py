@@ -83,7 +83,7 @@ def test_fer_matches_reference_points(handle, golden_dir):
 @pytest.mark.parametrize("tep_order,ebn0,flags,other_metric", [(0, 2.0, 0, False), (1, 3.0, 0, False), (0, 2.5, 3, True), (1, 2.5, 1, True)])
 def test_pair_sweep_equals_lut_sweep_on_a_million_frames(handle, tep_order, ebn0, flags, other_metric):
     """The tensor-core pair sweep (order-2 lists, truncated scores + exact re-scoring of the window) against the
-    exact 64-bit byte-LUT sweep of the same kernel family (block-minima path, one block = the whole list) on 2^20
+    exact 64-bit byte-LUT sweep of the same kernel family (block-minima path with LDPCB_BLOCKS_LUT=1, one block = the whole list) on 2^20
     device-generated frames: first-minimum index and exact score must agree on every frame.  With `other_metric` the
     scoring metric differs from the ordering metric (the DL path's shape: negative per-position deltas) and the tie /
     discrepancy flags are set."""
@@ -106,11 +106,69 @@ def test_pair_sweep_equals_lut_sweep_on_a_million_frames(handle, tep_order, ebn0
     bm = empty((B, 1), torch.int64)
     ba = empty((B, 1), torch.int32)
     ex2 = empty((B,), torch.int32)
-    handle.call("ldpcb_osd_block_minima", y, ys, B, dev(teps.view(np.int32)), len(teps), dev(starts), 1, flags, bm, ba, ex2, None, None, None, None)
-    sync()
+    import os
+
+    os.environ["LDPCB_BLOCKS_LUT"] = "1"
+    try:
+        handle.call("ldpcb_osd_block_minima", y, ys, B, dev(teps.view(np.int32)), len(teps), dev(starts), 1, flags, bm, ba, ex2, None, None, None, None)
+        sync()
+    finally:
+        os.environ.pop("LDPCB_BLOCKS_LUT", None)
     assert torch.equal(ex, ex2)
     assert torch.equal(bq, bm[:, 0])
     assert torch.equal(bt, ba[:, 0])
+
+
+@pytest.mark.parametrize("threshold_sum,quantised", [(2, False), (3, False), (3, True)])
+def test_block_minima_truncated_sweep_equals_lut_sweep_on_many_frames(code, threshold_sum, quantised):
+    """osd_blocks.cu (per-block truncated shuffle-table sweep + exact re-scoring of the window, marked blocks redone
+    through the byte LUT) against the byte-LUT sweep of round 1 (LDPCB_BLOCKS_LUT=1) on the NMS failures of 2^19 frames:
+    every block minimum and its first index, the transmitted codeword's score, exponent and permutation.  Blocks: the
+    DL order patterns over the six segments with total weight <= threshold_sum (27 / 77 blocks, 2081 / 43745 TEPs);
+    quantised LLRs make near-ties the rule, so most blocks go through the marked-block redo."""
+    import os
+
+    import torch
+
+    from short_ldpc_decoding_osd_b200 import _lib, globalmap as GL, nn_testing
+    from short_ldpc_decoding_osd_b200 import ordered_statistics_decoding as OSD
+    from tests.gpu_util import dev, empty, sync
+
+    for k, v in dict(code_parameters=code, threshold_sum=threshold_sum, segment_num=6, decoding_length=100).items():
+        GL.set_map(k, v)
+    teps_list, acc = nn_testing.generate_teps(OSD.osd(code), nn_testing.filter_order_patterns(nn_testing.convention_segment_path()))
+    packed = np.concatenate([OSD.pack_dl_teps(b) for b in teps_list])
+    nb = len(teps_list)
+    assert (nb, len(packed)) == ((27, 2081) if threshold_sum == 2 else (77, 43745))
+    h = _lib.Handle(code.H, code.G, device=0)
+    B = 1 << 19 if threshold_sum == 2 else 1 << 17
+    y = empty((B, 128), torch.float32)
+    tr = empty((B, 4), torch.int32)
+    h.call("ldpcb_gen_frames", 77, 0, B, 2.5, y, tr, None)
+    if quantised:
+        y = (torch.round(y * 2.0) / 2.0).contiguous()
+    bits, syn, met = empty((B, 4), torch.int32), empty((B,), torch.uint8), empty((B, 128), torch.float32)
+    h.call("ldpcb_nms_decode_fir", y, B, 12, 0.66943514, 1.0, 1.0, np.full(13, 1 / 13, np.float32), 0.0, bits, syn, met, None)
+    m = syn.bool()
+    yf, mf, tf = y[m].contiguous(), met[m].contiguous(), tr[m].contiguous()
+    n = int(yf.shape[0])
+    assert n > 1000
+    out = {}
+    for tag in ("sweep32", "lut"):
+        if tag == "lut":
+            os.environ["LDPCB_BLOCKS_LUT"] = "1"
+        try:
+            bm, ba, ex, ts, pm = empty((n, nb), torch.int64), empty((n, nb), torch.int32), empty((n,), torch.int32), empty((n,), torch.int64), empty((n, 128), torch.uint8)
+            h.call("ldpcb_osd_block_minima", mf, yf, n, dev(packed.view(np.int32)), len(packed), dev(np.asarray(acc, np.int32)), nb,
+                   OSD.FLAGS_DL | (threshold_sum << _lib.OSD_MAXW_SHIFT), bm, ba, ex, tf, ts, pm, None)
+            sync()
+            out[tag] = [x.cpu().numpy() for x in (bm, ba, ex, ts, pm)]
+        finally:
+            os.environ.pop("LDPCB_BLOCKS_LUT", None)
+    for name, u, v in zip(("block_min_q", "block_arg", "score_exp", "truth_score_q", "perm"), out["sweep32"], out["lut"]):
+        assert np.array_equal(u, v), (name, int((u != v).sum()), n)
+    assert (out["sweep32"][0] >= 0).all()
+    h.close()
 
 
 def test_order3_tensor_sweep_equals_generic_sweep_on_many_frames(code):
