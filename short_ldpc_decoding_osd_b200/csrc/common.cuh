@@ -81,7 +81,7 @@ struct ldpcb_handle {
     uint8_t G[ldpcb::K * ldpcb::N];
     ldpcb::NmsTables nms_host;
     ldpcb::NmsTables* nms_dev = nullptr;
-    uint64_t* gcol_dev = nullptr;  // [128] column j of G, bit r = G[r][j]
+    uint64_t* gcol_dev = nullptr;  // [0,128): column j of G, bit r = G[r][j]; [128,256): unit-column flags (handle.cu)
     uint64_t gcol_host[ldpcb::N];
     ldpcb::TepTable tep[4][2];      // [order][tep_order]
     int32_t* one_block_dev = nullptr;  // {0, n} scratch for single-block calls

@@ -328,8 +328,21 @@ static int build_code_tables(ldpcb_handle* h) {
     }
     LDPCB_CUDA(h, cudaMalloc(&h->nms_dev, sizeof(NmsTables)));
     LDPCB_CUDA(h, cudaMemcpy(h->nms_dev, &t, sizeof(NmsTables), cudaMemcpyHostToDevice));
-    LDPCB_CUDA(h, cudaMalloc(&h->gcol_dev, sizeof(uint64_t) * N));
-    LDPCB_CUDA(h, cudaMemcpy(h->gcol_dev, h->gcol_host, sizeof(uint64_t) * N, cudaMemcpyHostToDevice));
+    {
+        // [0, N): the columns; [N, 2N): 1 for the unit columns the OSD elimination may treat as such -- one per generator
+        // row (the first in index order), see osd_prepare.cuh step 2
+        uint64_t tab[2 * N];
+        memcpy(tab, h->gcol_host, sizeof(uint64_t) * N);
+        uint64_t rows_seen = 0;
+        for (int j = 0; j < N; ++j) {
+            const uint64_t c = h->gcol_host[j];
+            const bool unit = c != 0 && (c & (c - 1)) == 0 && !(rows_seen & c);
+            if (unit) rows_seen |= c;
+            tab[N + j] = unit ? 1 : 0;
+        }
+        LDPCB_CUDA(h, cudaMalloc(&h->gcol_dev, sizeof tab));
+        LDPCB_CUDA(h, cudaMemcpy(h->gcol_dev, tab, sizeof tab, cudaMemcpyHostToDevice));
+    }
     return LDPCB_OK;
 }
 

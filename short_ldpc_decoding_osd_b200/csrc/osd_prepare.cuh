@@ -265,85 +265,154 @@ __device__ __forceinline__ Prep prepare_frame(const OsdArgs& a, FrameSm& F, cons
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) F.pi1[rank[k]] = (unsigned char)(4 * lane + k);
-            __syncwarp();
-            const unsigned w = reinterpret_cast<const unsigned*>(F.pi1)[lane];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) idx[k] = (w >> (8 * k)) & 0xffu;
         } else {
             reinterpret_cast<unsigned*>(F.pi1)[lane] = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
         }
-        // ---- 2. GF(2) elimination, column-major ----------------------------------------------
-        unsigned clo[4], chi[4];  // columns as two 32-bit halves: every step works on one half with 32-bit ops
+        __syncwarp();
+        // ---- 2. GF(2) elimination, column-major; from here on a lane holds the sorted positions lane + 32k --------------
+        // Columns as two 32-bit halves (every step works on one half with 32-bit ops).  `info` marks the unit columns of
+        // G (gcol[N + j] != 0: one per generator row, the handle picks them): such a column stays a unit vector until
+        // another column takes its row as pivot, and while it is one it joins the basis without any row operation.  The
+        // scan therefore VISITS only the other ("parity") columns of the 64 most reliable positions -- about half -- and
+        // lets them choose their pivot among the rows no unit column of those 64 positions owns (any unused row with a 1
+        // gives the same basis and, the reduced matrix being unique for a basis, the same P').  Only a column without a 1
+        // there takes the exact set of free rows and, if it takes the row of a later unit column, puts that column on the
+        // visit list.  Positions 64.. are scanned one by one as before (a handful until the basis is complete).
+        unsigned clo[4], chi[4];
+        bool info[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const unsigned long long g = gcol[idx[k]];
+            const unsigned o = F.pi1[lane + 32 * k];
+            const unsigned long long g = gcol[o];
+            info[k] = gcol[N + o] != 0ull;
             clo[k] = (unsigned)g;
             chi[k] = (unsigned)(g >> 32);
         }
+        unsigned pvb[4] = {0u, 0u, 0u, 0u};  // pivot-row bit (within its 32-bit half) of my column k, 0 = not a pivot
+        unsigned pvh = 0u;                   // bit k: that row lies in the high half
         {
-            unsigned used_lo = 0u, used_hi = 0u;
-            int npiv = 0, l = 0;
-            unsigned pvb[4] = {0u, 0u, 0u, 0u};  // pivot-row bit (within its 32-bit half) of my column k, 0 = not a pivot
-            unsigned pvh = 0u;                   // bit k: that row lies in the high half
-            // Once the basis is complete no row is free, so the remaining columns of a group of four fall through as
-            // dependent, which is what they are: the count is only tested once per group.  The loop keeps no lists:
-            // the owner lane notes its pivots and the MRB / LRB position lists are built afterwards by a prefix sum.
-            for (; l < 32 && npiv < K; ++l) {
-                const bool mine = (lane == l);
+            // rows owned by the unit columns of positions 0..63
+            const unsigned own_lo = __reduce_or_sync(0xffffffffu, (info[0] ? clo[0] : 0u) | (info[1] ? clo[1] : 0u));
+            const unsigned own_hi = __reduce_or_sync(0xffffffffu, (info[0] ? chi[0] : 0u) | (info[1] ? chi[1] : 0u));
+            unsigned used_lo = 0u, used_hi = 0u;        // pivot rows of the visited columns
+            unsigned av_lo = ~own_lo, av_hi = ~own_hi;  // rows no unit column of positions 0..63 owns, minus the used ones
+            unsigned extra1 = 0u;                       // unit columns of positions 32..63 that lost their row
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const unsigned cl = __shfl_sync(0xffffffffu, clo[k], l);
-                    const unsigned ch = __shfl_sync(0xffffffffu, chi[k], l);
-                    const unsigned al = cl & ~used_lo, ah = ch & ~used_hi;
-                    if ((al | ah) != 0u) {  // else: dependent on more reliable columns
-                        if (al != 0u) {  // pivot row in the low word (any unused row with a 1 gives the same basis)
-                            const unsigned bit = al & (0u - al);
-                            used_lo |= bit;
-                            const unsigned ml = cl ^ bit;
-                            if ((ml | ch) != 0u) {  // an untouched unit column (information position of G) needs no row operation
+            for (int k = 0; k < 2; ++k) {
+                unsigned todo = __ballot_sync(0xffffffffu, !info[k]) | (k == 1 ? extra1 : 0u);
+                while (todo != 0u) {  // warp-uniform
+                    const int ll = __ffs(todo) - 1;
+                    todo &= todo - 1u;
+                    const unsigned cl = __shfl_sync(0xffffffffu, clo[k], ll);
+                    const unsigned ch = __shfl_sync(0xffffffffu, chi[k], ll);
+                    unsigned al = cl & av_lo, ah = ch & av_hi;
+                    bool exact = false;
+                    if ((al | ah) == 0u) {
+                        // no 1 in the rows above: the exact free rows = not used and not owned by a unit column at an
+                        // earlier position (that column is in the basis on its own row, or lost the row to a used one)
+                        unsigned rl = 0u, rh = 0u;
 #pragma unroll
-                                for (int kk = 0; kk < 4; ++kk) xor_if_bit(clo[kk], chi[kk], clo[kk], bit, ml, ch);
-                            }
-                            if (mine) pvb[k] = bit;
-                        } else {
-                            const unsigned bit = ah & (0u - ah);
-                            used_hi |= bit;
-                            const unsigned mh = ch ^ bit;
-                            if ((cl | mh) != 0u) {
-#pragma unroll
-                                for (int kk = 0; kk < 4; ++kk) xor_if_bit(clo[kk], chi[kk], chi[kk], bit, cl, mh);
-                            }
-                            if (mine) { pvb[k] = bit; pvh |= 1u << k; }
+                        for (int kk = 0; kk <= k; ++kk) {
+                            const bool before = info[kk] && (kk < k || lane < ll);
+                            rl |= before ? clo[kk] : 0u;
+                            rh |= before ? chi[kk] : 0u;
                         }
-                        ++npiv;
+                        al = cl & ~(used_lo | __reduce_or_sync(0xffffffffu, rl));
+                        ah = ch & ~(used_hi | __reduce_or_sync(0xffffffffu, rh));
+                        if ((al | ah) == 0u) continue;  // dependent on more reliable columns
+                        exact = true;
+                    }
+                    unsigned bit_lo = 0u, bit_hi = 0u;
+                    if (al != 0u) {
+                        bit_lo = al & (0u - al);
+                        used_lo |= bit_lo;
+                        av_lo &= ~bit_lo;
+                        const unsigned ml = cl ^ bit_lo;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) xor_if_bit(clo[kk], chi[kk], clo[kk], bit_lo, ml, ch);
+                        if (lane == ll) pvb[k] = bit_lo;
+                    } else {
+                        bit_hi = ah & (0u - ah);
+                        used_hi |= bit_hi;
+                        av_hi &= ~bit_hi;
+                        const unsigned mh = ch ^ bit_hi;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) xor_if_bit(clo[kk], chi[kk], chi[kk], bit_hi, cl, mh);
+                        if (lane == ll) { pvb[k] = bit_hi; pvh |= 1u << k; }
+                    }
+                    if (exact) {
+                        // the row may belong to a unit column further down positions 0..63 (the row operation above has
+                        // just changed it): it is an ordinary column from now on and gets its visit
+#pragma unroll
+                        for (int kk = k; kk < 2; ++kk) {
+                            const bool lost = info[kk] && (((clo[kk] & bit_lo) | (chi[kk] & bit_hi)) != 0u);
+                            const unsigned m = __ballot_sync(0xffffffffu, lost);
+                            if (lost) info[kk] = false;
+                            if (kk == k) todo |= m; else extra1 |= m;
+                        }
                     }
                 }
             }
-            // position lists: MRB = pivot columns, LRB = the others, both in scan (reliability) order
-            const int cnt = (pvb[0] != 0u) + (pvb[1] != 0u) + (pvb[2] != 0u) + (pvb[3] != 0u);
-            int pre = cnt;
+            // the unit columns of positions 0..63 that kept their row: pivots on it
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, pre, d);
-                if (lane >= d) pre += t;
+            for (int k = 0; k < 2; ++k) {
+                if (info[k]) {
+                    pvb[k] = clo[k] | chi[k];
+                    if (clo[k] == 0u) pvh |= 1u << k;
+                }
             }
-            int r = pre - cnt;      // pivots before my first column
-            int q = 4 * lane - r;   // non-pivots before my first column
+            // positions 64..127 one by one; every row a unit column above owns is used (by it or by the column that took it)
+            used_lo |= own_lo;
+            used_hi |= own_hi;
+            int npiv = __popc(used_lo) + __popc(used_hi);
+#pragma unroll
+            for (int k = 2; k < 4; ++k) {
+                for (int ll = 0; ll < 32 && npiv < K; ++ll) {
+                    const unsigned cl = __shfl_sync(0xffffffffu, clo[k], ll);
+                    const unsigned ch = __shfl_sync(0xffffffffu, chi[k], ll);
+                    const unsigned al = cl & ~used_lo, ah = ch & ~used_hi;
+                    if ((al | ah) == 0u) continue;  // dependent on more reliable columns
+                    if (al != 0u) {
+                        const unsigned bit = al & (0u - al);
+                        used_lo |= bit;
+                        const unsigned ml = cl ^ bit;
+                        if ((ml | ch) != 0u) {  // a unit column needs no row operation
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) xor_if_bit(clo[kk], chi[kk], clo[kk], bit, ml, ch);
+                        }
+                        if (lane == ll) pvb[k] = bit;
+                    } else {
+                        const unsigned bit = ah & (0u - ah);
+                        used_hi |= bit;
+                        const unsigned mh = ch ^ bit;
+                        if ((cl | mh) != 0u) {
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) xor_if_bit(clo[kk], chi[kk], chi[kk], bit, cl, mh);
+                        }
+                        if (lane == ll) { pvb[k] = bit; pvh |= 1u << k; }
+                    }
+                    ++npiv;
+                }
+            }
+            // position lists: MRB = pivot columns, LRB = the others, both in scan (reliability) order
+            const unsigned lt = (1u << lane) - 1u;
+            int base = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const unsigned char c = (unsigned char)(4 * lane + k);
+                const unsigned bal = __ballot_sync(0xffffffffu, pvb[k] != 0u);
+                const int r = base + __popc(bal & lt);  // pivots before this position
+                const int p = 32 * k + lane;
                 if (pvb[k] != 0u) {
-                    F.pos[r] = c;
+                    F.pos[r] = (unsigned char)p;
                     F.prow_of[r] = (unsigned char)(((pvh >> k) & 1u) * 32u + 31u - __clz(pvb[k]));
-                    ++r;
                 } else {
-                    F.pos[K + q] = c;
-                    ++q;
+                    F.pos[K + p - r] = (unsigned char)p;
                 }
+                base += __popc(bal);
             }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) cols[4 * lane + k] = ((unsigned long long)chi[k] << 32) | clo[k];
+        for (int k = 0; k < 4; ++k) cols[lane + 32 * k] = ((unsigned long long)chi[k] << 32) | clo[k];
         __syncwarp();
         // ---- permutation pi2 o pi1 -----------------------------------------------------------
 #pragma unroll
