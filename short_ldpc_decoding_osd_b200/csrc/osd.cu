@@ -55,11 +55,13 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_kernel(OsdArgs a, const ui
     OsdTally tally;
 
     for (int64_t f0 = (int64_t)blockIdx.x * OSD_FPB; f0 < nframes; f0 += (int64_t)gridDim.x * OSD_FPB) {
-        const int64_t f = f0 + warp;
-        const bool active = f < nframes;
-        const int64_t row = active ? (a.idx ? (int64_t)a.idx[f] : f) : 0;
-        Prep P = {};
-        if (active) P = prepare_frame<BLOCKS>(a, F, gcol, row, f, lane, ties_high, disc_from_score);
+        // A warp past the end of the list (last round only) prepares the last frame again and writes nothing: without a
+        // per-warp condition around prepare and sweep the compiler sees converged code (no BSSY / BRA.DIV around the
+        // shuffles and votes)
+        const bool active = f0 + warp < nframes;
+        const int64_t f = active ? f0 + warp : nframes - 1;
+        const int64_t row = a.idx ? (int64_t)a.idx[f] : f;
+        const Prep P = prepare_frame<BLOCKS>(a, F, gcol, row, f, lane, ties_high, disc_from_score);
         const unsigned char* pm = P.pm;
         const unsigned long long* myprow = P.myprow;
         const unsigned long long hd_lrb = P.hd_lrb, ho_mrb = P.ho_mrb, d0 = P.d0;
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_kernel(OsdArgs a, const ui
         // ---- 5./6. sweep: the four warps take the prepared frames in turn -------------------------------------
         long long solo_s = 0x7fffffffffffffffll;
         int solo_i = 0x7fffffff;
-        if (!BLOCKS && active) {
+        if (!BLOCKS) {
             if (!SOLO && lane == 0) { S.cand_n[warp] = 0; S.cand_ovf[warp] = 0; }
             __syncwarp();
             // 5-bit chunk tables of the 32-bit LRB weights: tabs[j][e] = sum of w32[5j+i] over the set bits i of e
@@ -210,7 +212,9 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_kernel(OsdArgs a, const ui
         }
         if (!SOLO) __syncthreads();  // all partial minima written; all LUT reads done
         // ---- outputs (each warp finishes its own frame) ---------------------------------------------------
-        if (active) {
+        // SOLO: a warp past the end has the last frame's results and stores them again (the loop body stays free of
+        // per-warp conditions); otherwise its frame was not swept and it has nothing to write
+        if (SOLO || active) {
             if (!BLOCKS) {
                 long long best_s = 0x7fffffffffffffffll;
                 int best_i = 0x7fffffff;
@@ -270,7 +274,7 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_kernel(OsdArgs a, const ui
                 const int64_t orow = a.idx ? row : f;
                 const unsigned wv = lane == 0 ? wout[0] : lane == 1 ? wout[1] : lane == 2 ? wout[2] : wout[3];
                 if (lane < 4 && a.cw_bits) a.cw_bits[orow * 4 + lane] = wv;
-                if (a.tally_truth) osd_tally_frame(tally, a, orow, wv, best_i, lane);
+                if (a.tally_truth && active) osd_tally_frame(tally, a, orow, wv, best_i, lane);
                 if (lane == 0) {
                     if (a.best_tep) a.best_tep[orow] = best_i;
                     if (a.best_score_q) a.best_score_q[orow] = best_s;
@@ -288,6 +292,7 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_kernel(OsdArgs a, const ui
         }
         // the next round's prepare overwrites fr[] and red_*: every warp has passed the barrier above and
         // only touches its own FrameSm until the next barrier
+        if (SOLO) __syncthreads();  // not needed for the data: a CTA barrier in the loop is what lets the compiler treat the body as converged code (25 BRA.DIV and half of the BSSY/BSYNC pairs go away)
     }
     if (!BLOCKS && a.tally_truth) osd_tally_flush(tally, a, lane);
 }
@@ -328,16 +333,13 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_fs_kernel(OsdArgs a, FsParams
     const int cls_start[5] = {0, 1, 65, 2081, 43745};
 
     for (int64_t f0 = (int64_t)blockIdx.x * OSD_FPB; f0 < nframes; f0 += (int64_t)gridDim.x * OSD_FPB) {
-        const int64_t f = f0 + warp;
-        const bool active = f < nframes;
-        const int64_t row = active ? (a.idx ? (int64_t)a.idx[f] : f) : 0;
-        Prep P = {};
-        if (active) {
-            P = prepare_frame<false>(a, F, gcol, row, f, lane, false, false);
-            if (lane == 0) {
-                const double sh = (double)fp.beta_shift * __hiloint2double((1023 + 54 - P.E) << 20, 0);
-                S.fs_score[warp] = sh >= 4.6e18 ? (1ll << 62) : __double2ll_rn(sh);
-            }
+        const bool active = f0 + warp < nframes;  // a warp past the end prepares the last frame again (see osd_kernel)
+        const int64_t f = active ? f0 + warp : nframes - 1;
+        const int64_t row = a.idx ? (int64_t)a.idx[f] : f;
+        const Prep P = prepare_frame<false>(a, F, gcol, row, f, lane, false, false);
+        if (lane == 0) {
+            const double sh = (double)fp.beta_shift * __hiloint2double((1023 + 54 - P.E) << 20, 0);
+            S.fs_score[warp] = sh >= 4.6e18 ? (1ll << 62) : __double2ll_rn(sh);
         }
         const int nfr = (int)((nframes - f0) < OSD_FPB ? (nframes - f0) : OSD_FPB);
         for (int w = 0; w < nfr; ++w) {

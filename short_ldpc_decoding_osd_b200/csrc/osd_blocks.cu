@@ -38,11 +38,12 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_blocks_kernel(OsdArgs a, c
     const int nb = a.n_blocks;
 
     for (int64_t f0 = (int64_t)blockIdx.x * OSD_FPB; f0 < nframes; f0 += (int64_t)gridDim.x * OSD_FPB) {
-        const int64_t f = f0 + warp;
-        const bool active = f < nframes;
-        const int64_t row = active ? (a.idx ? (int64_t)a.idx[f] : f) : 0;
+        // a warp past the end of the list (last round only) redoes the last frame and stores the same values again: no
+        // per-warp condition around the body, so the compiler sees converged code
+        const int64_t f = f0 + warp < nframes ? f0 + warp : nframes - 1;
+        const int64_t row = a.idx ? (int64_t)a.idx[f] : f;
         bool marked = false;
-        if (active) {
+        {
             const Prep P = prepare_frame<true>(a, F, gcol, row, f, lane, ties_high, disc_from_score);
             __syncwarp();
             int tb[13];

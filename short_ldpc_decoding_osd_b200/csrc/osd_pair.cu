@@ -46,14 +46,17 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_pair_kernel(OsdArgs a, con
     }
 
     for (int64_t f0 = (int64_t)blockIdx.x * OSD_FPB; f0 < nframes; f0 += (int64_t)gridDim.x * OSD_FPB) {
-        const int64_t f = f0 + warp;
-        const bool active = f < nframes;
-        const int64_t row = active ? (a.idx ? (int64_t)a.idx[f] : f) : 0;
+        // A warp past the end of the list (last round only) redoes the last frame and writes the same results again: no
+        // per-warp condition around the body, so the compiler sees converged code (no BSSY / BRA.DIV around every
+        // shuffle and vote)
+        const bool active = f0 + warp < nframes;
+        const int64_t f = active ? f0 + warp : nframes - 1;
+        const int64_t row = a.idx ? (int64_t)a.idx[f] : f;
         Prep P = {};
         long long best_s = 0x7fffffffffffffffll;
         int best_i = 0x7fffffff;
         bool fallback = false;
-        if (active) {
+        {
             P = prepare_frame<false, PAIR_SH>(a, F, gcol, row, f, lane, ties_high, disc_from_score);
             const unsigned long long d0 = P.d0;
             __syncwarp();
@@ -227,7 +230,7 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_pair_kernel(OsdArgs a, con
             }
             __syncthreads();  // red_* and the LUT are free for the next fallback frame
         }
-        // ---- outputs (each warp finishes its own frame) -------------------------------------------------------------
+        // ---- outputs (each warp finishes its own frame; a warp past the end has nothing to write) ----------------------
         if (active) {
             unsigned long long D = P.d0, flip = 0ull;
             if (best_i != 0x7fffffff) {

@@ -296,3 +296,54 @@ def test_other_code_nms_and_osd(code):
         assert int(cnt[0]) == B and int(cnt[9]) == int((want != cw).any(1).sum())
     finally:
         h.close()
+
+
+@pytest.mark.parametrize("mixed_rows", [64, 32, 5])
+def test_osd_does_not_depend_on_the_generator_form(handle, code, mixed_rows):
+    """The OSD elimination treats the unit columns of G specially (osd_prepare.cuh step 2).  The MRB, the reduced
+    matrix and the decision depend on the code and the frame only, so a handle built on T.G -- T invertible, mixing
+    `mixed_rows` generator rows, which leaves 64 - mixed_rows unit columns (none for 64) -- must reproduce every output
+    of the systematic handle bit for bit; a few frames are also checked against the oracle run on T.G."""
+    rng = np.random.default_rng(100 + mixed_rows)
+    G = np.asarray(code.G, dtype=np.uint8)
+    while True:
+        T = np.eye(64, dtype=np.uint8)
+        T[:mixed_rows, :mixed_rows] = rng.integers(0, 2, (mixed_rows, mixed_rows), dtype=np.uint8)
+        G2 = (T.astype(np.int64) @ G.astype(np.int64) % 2).astype(np.uint8)
+        if _gf2_rank(G2) == 64:
+            break
+    unit_cols = int(((G2.sum(0) == 1)).sum())
+    assert unit_cols <= 64 - mixed_rows + 2
+    y, cw = failing_frames(code, 1500, seed=91)
+    y = np.ascontiguousarray(y)
+    h2 = _lib.Handle(code.H, G2, device=0)
+    try:
+        for order, flags in ((1, 0), (2, 0), (2, 1)):
+            a = osd_gpu(handle, y, order=order, flags=flags)
+            b = osd_gpu(h2, y, order=order, flags=flags)
+            for key in ("perm", "redG", "score_exp", "best_tep", "best_score_q", "codeword"):
+                assert np.array_equal(a[key], b[key]), (key, order, flags)
+        teps = OO.generate_teps_conv(1)
+        b = osd_gpu(h2, y[:6], order=1)
+        for i in range(6):
+            check_osd_frame(b, i, OO.osd_frame(y[i], y[i], G2, teps), code)
+    finally:
+        h2.close()
+
+
+def _gf2_rank(M):
+    A = np.array(M, dtype=np.uint8) & 1
+    r = 0
+    for c in range(A.shape[1]):
+        p = np.flatnonzero(A[r:, c])
+        if len(p) == 0:
+            continue
+        p = p[0] + r
+        A[[r, p]] = A[[p, r]]
+        hit = np.flatnonzero(A[:, c])
+        hit = hit[hit != r]
+        A[hit] ^= A[r]
+        r += 1
+        if r == A.shape[0]:
+            break
+    return r
