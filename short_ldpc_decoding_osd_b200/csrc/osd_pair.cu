@@ -2,7 +2,8 @@
 //
 // The sweep is the tensor-core pair sweep described in osd_sweep.cuh / DESIGN.md 4.2 (score of the pair TEP {i,j} =
 // R_i + C_j - 2 M[i][j], M a 64x64x64 u8 matrix product on IMMA.16832.U8.U8), organised per warp: the 20 16x8 tiles
-// that hold a pair i < j are visited in turn, four A-fragment builds and twenty B-fragment builds per frame.  A CTA of
+// that hold a pair i < j are visited in turn, four A-fragment builds per frame, the eight B fragments built once into
+// shared memory (the space of the fallback LUT).  An element's accumulator starts at -(R_i + C_j) and ends at -S.  A CTA of
 // four warps shares nothing but the 16 KB byte LUT of the rare exact fallback (a frame whose truncated scores leave
 // too many candidates, e.g. quantised inputs), so a round costs two CTA barriers instead of thirteen.
 // Replaces the same reference code as osd.cu (swapped_info / identify_mrb / full_gf2elim / convention_osd_main).
@@ -13,7 +14,10 @@
 namespace ldpcb {
 
 struct __align__(16) PairSmem {
-    unsigned long long lut[8][256];  // exact fallback only
+    union {
+        unsigned long long lut[8][256];  // exact fallback (after barrier (A): the sweeps are over)
+        uint4 bfrag[OSD_FPB][8][32];     // sweep: [warp][column block nj][lane] B fragment registers, built once per frame
+    };
     FrameSm fr[OSD_FPB];
     long long red_s[OSD_FPB];        // fallback: per-warp partial minima of the frame in turn
     int red_i[OSD_FPB];
@@ -21,9 +25,13 @@ struct __align__(16) PairSmem {
 };
 
 constexpr int PW_CODE_SINGLE = 80, PW_CODE_EMPTY = 82;  // codes 0..79: (tile << 2) | element
-constexpr int PW_PEN = 16384;  // x 65536 = 2^30 on the packed score of an excluded element (real packed scores stay below 2^30)
+constexpr int PW_PEN = 1 << 29;  // an excluded element's accumulator (-S) starts this much lower: it never reaches a gate (S < 2^23)
 // packed scores (S << 7 | code) that can still be inside the truncation window when the minimum is m
 __device__ __forceinline__ int pw_gate(int m) { return m > 0x7fffffff - ((OSD_WIN + 1) << 7) ? 0x7fffffff : ((((m >> 7) + OSD_WIN) << 7) | 127); }
+// the tiles hold -S: packed score <= gate  <=>  S <= gate >> 7  <=>  -S >= -(gate >> 7)   (the low seven bits of a gate are ones)
+__device__ __forceinline__ int pw_gate_neg(int gate) { return -(gate >> 7); }
+// four bits -> four bytes of 0/2 (bit k of the nibble in byte k): B operand of the low weight plane, x 64 = of the high one
+__device__ __forceinline__ unsigned spread4x2(unsigned word, int sh) { return (((word >> sh) & 0xFu) * 0x00408102u) & 0x02020202u; }
 
 __global__ void __launch_bounds__(OSD_THREADS, 6) osd_pair_kernel(OsdArgs a, const uint64_t* __restrict__ gcol) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -57,10 +65,10 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_pair_kernel(OsdArgs a, con
         int best_i = 0x7fffffff;
         bool fallback = false;
         {
-            P = prepare_frame<false, PAIR_SH>(a, F, gcol, row, f, lane, ties_high, disc_from_score);
+            P = prepare_frame<false, PAIR1_SH>(a, F, gcol, row, f, lane, ties_high, disc_from_score);
             const unsigned long long d0 = P.d0;
             __syncwarp();
-            // ---- R_i, C_j and the empty TEP through the shuffle tables; weight byte planes --------------------
+            // ---- R_i, C_j and the empty TEP through the shuffle tables; weight byte planes; B fragments ----------
             int tb[13];
             build_shfl_tables(F, lane, tb);
             int s0 = 0x7fffffff, s1 = 0x7fffffff;
@@ -73,15 +81,22 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_pair_kernel(OsdArgs a, con
                 const int c1 = qb + wpop_shfl(tb, P.myprow[1]);
                 const unsigned wa = F.w32[lane], wb = F.w32[lane + 32];
                 __syncwarp();  // every lane is done with yo/ys and w32: reuse yo/ys
-                int* RCw = reinterpret_cast<int*>(F.yo);
-                RCw[lane] = r0 << 7; RCw[lane + 32] = r1 << 7;
-                RCw[64 + lane] = c0 << 7; RCw[96 + lane] = c1 << 7;
-                unsigned char* wq = reinterpret_cast<unsigned char*>(F.ys);  // [plane][LRB position]
+                int* RCw = reinterpret_cast<int*>(F.yo);  // -R_i, -C_j: the accumulators start at -(R_i + C_j)
+                RCw[lane] = -r0; RCw[lane + 32] = -r1;
+                RCw[64 + lane] = -c0; RCw[96 + lane] = -c1;
+                unsigned char* wq = reinterpret_cast<unsigned char*>(F.ys);  // [plane][LRB position]; w < 2^14
                 wq[lane] = (unsigned char)(wa & 0xffu); wq[lane + 32] = (unsigned char)(wb & 0xffu);
-                wq[64 + lane] = (unsigned char)(wa >> 8); wq[96 + lane] = (unsigned char)(wb >> 8);
+                wq[64 + lane] = (unsigned char)((wa >> 8) << 2); wq[96 + lane] = (unsigned char)((wb >> 8) << 2);
                 track2(s0, s1, (r0 << 7) | PW_CODE_SINGLE);
                 track2(s0, s1, (r1 << 7) | (PW_CODE_SINGLE + 1));
                 if (lane == 0) track2(s0, s1, (z << 7) | PW_CODE_EMPTY);
+            }
+            uint4* Bc = &S.bfrag[warp][0][0];
+#pragma unroll
+            for (int x = 0; x < 8; ++x) {  // column j = 8x + g, this thread's nibbles of P'_j
+                const unsigned long long cj = F.prow[8 * x + g];
+                Bc[32 * x + lane] = make_uint4(spread4x2((unsigned)cj, 4 * t), spread4x2((unsigned)cj, 4 * t + 16),
+                                               spread4x2((unsigned)(cj >> 32), 4 * t), spread4x2((unsigned)(cj >> 32), 4 * t + 16));
             }
             __syncwarp();
             // ---- the 20 tiles ---------------------------------------------------------------------------
@@ -96,13 +111,14 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_pair_kernel(OsdArgs a, con
                     for (int hh = 0; hh < 2; ++hh) wr[p][kk][hh] = wqw[16 * p + 8 * kk + 4 * hh + t];
             int code = 0;
             int gate = pw_gate(__reduce_min_sync(0xffffffffu, s0));  // the singles and the empty TEP are tracked already
+            int gn = pw_gate_neg(gate);
 #pragma unroll 1
             for (int mi = 0; mi < 4; ++mi) {
                 // masked weights of rows 16mi+g and +8
                 unsigned afr[2][2][4];  // [k half][plane][fragment register]
                 const int i0 = 16 * mi + g;
                 const unsigned long long u0 = d0 ^ F.prow[i0], u1 = d0 ^ F.prow[i0 + 8];
-                const int rr0 = RC[i0], rr1 = RC[i0 + 8];
+                const int nr0 = RC[i0], nr1 = RC[i0 + 8];
 #pragma unroll
                 for (int kk = 0; kk < 2; ++kk) {
                     const unsigned w0 = kk ? (unsigned)(u0 >> 32) : (unsigned)u0;
@@ -118,36 +134,29 @@ __global__ void __launch_bounds__(OSD_THREADS, 6) osd_pair_kernel(OsdArgs a, con
                         }
                     }
                 }
-                // One 16x8 tile.  The triangle i < j costs nothing: the two tiles of a row block that touch the diagonal start
-                // their high-plane accumulators at -PW_PEN on the elements with i >= j (the packed score comes out 2^30 too
-                // large).  A thread's two smallest scores are tracked behind a warp-uniform gate (running warp minimum +
-                // truncation window): every score that can still be a candidate at the end passes it.
+                // One 16x8 tile, ONE accumulator per element: it starts at -(R_i + C_j) and the four IMMAs add 2 M[i][j] --
+                // the low plane against B bytes of 2, the high plane (bytes (w >> 8) << 2) against B bytes of 128 -- so it
+                // ends as -S(i,j) with no arithmetic after the product.  The triangle i < j costs nothing either: the two
+                // tiles of a row block that touch the diagonal start 2^29 lower on the elements with i >= j.  A thread's
+                // two smallest scores are tracked behind a warp-uniform gate (running warp minimum + truncation window):
+                // every score that can still be a candidate at the end passes it.
                 auto tile = [&](int nj, const int (&pen)[4]) {
-                    const unsigned long long cj = F.prow[8 * nj + g];
-                    unsigned bfr[2][2];
-#pragma unroll
-                    for (int kk = 0; kk < 2; ++kk)
-#pragma unroll
-                        for (int hh = 0; hh < 2; ++hh)
-                            bfr[kk][hh] = spread4(kk ? (unsigned)(cj >> 32) : (unsigned)cj, 4 * t + 16 * hh);
-                    int acc[2][4] = {{0, 0, 0, 0}, {pen[0], pen[1], pen[2], pen[3]}};
-#pragma unroll
-                    for (int kk = 0; kk < 2; ++kk)
-#pragma unroll
-                        for (int p = 0; p < 2; ++p) imma_u8(acc[p], afr[kk][p], bfr[kk]);
+                    const uint4 bf = Bc[32 * nj + lane];
+                    const unsigned bl0[2] = {bf.x, bf.y}, bl1[2] = {bf.z, bf.w};
+                    const unsigned bh0[2] = {bf.x << 6, bf.y << 6}, bh1[2] = {bf.z << 6, bf.w << 6};
                     const int2 cc = *reinterpret_cast<const int2*>(RC + 64 + 8 * nj + 2 * t);
-                    int p4[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int rc = ((e >> 1) ? rr1 : rr0) + ((e & 1) ? cc.y : cc.x) + (code + e);
-                        p4[e] = rc - 256 * acc[0][e] - 65536 * acc[1][e];  // ((R + C - 2M) << 7) | code
-                    }
-                    const int m4 = min(min(p4[0], p4[1]), min(p4[2], p4[3]));
-                    if (__any_sync(0xffffffffu, m4 <= gate)) {
+                    int acc[4] = {nr0 + cc.x + pen[0], nr0 + cc.y + pen[1], nr1 + cc.x + pen[2], nr1 + cc.y + pen[3]};
+                    imma_u8(acc, afr[0][0], bl0);
+                    imma_u8(acc, afr[0][1], bh0);
+                    imma_u8(acc, afr[1][0], bl1);
+                    imma_u8(acc, afr[1][1], bh1);
+                    const int m4 = max(max(acc[0], acc[1]), max(acc[2], acc[3]));
+                    if (__any_sync(0xffffffffu, m4 >= gn)) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
-                            if (p4[e] <= gate) track2(s0, s1, p4[e]);
+                            if (acc[e] >= gn) track2(s0, s1, ((-acc[e]) << 7) | (code + e));
                         gate = pw_gate(__reduce_min_sync(0xffffffffu, s0));
+                        gn = pw_gate_neg(gate);
                     }
                     code += 4;
                 };

@@ -82,7 +82,10 @@ __device__ __forceinline__ long long score64(const unsigned long long (*lut)[256
 // tables.  Scores are packed as (S << 7) | code (code = tile and element, or a single / the empty TEP), so a thread
 // tracks its minimum and second minimum with three integer min/max per element; the candidates within the
 // truncation window of the minimum are re-scored exactly as in the generic sweep (kernel: osd_pair.cu).
-constexpr int PAIR_SH = 38;  // w = floor(q / 2^38) < 2^16: two byte planes; window = 72 * 2^38 ~ 2^-9 of the largest |y|
+constexpr int PAIR_SH = 38;  // osd3.cu: w = floor(q / 2^38) < 2^16: two byte planes; window = 72 * 2^38 ~ 2^-9 of the largest |y|
+// osd_pair.cu: w = floor(q / 2^40) < 2^14 so that BOTH planes accumulate into one s32 per element: 2 M = sum (w & 255) * (2 b)
+// + sum ((w >> 8) << 2) * (128 b), every operand a u8; window = 72 * 2^40 ~ 2^-7.8 of the largest |y|
+constexpr int PAIR1_SH = 40;
 __device__ __forceinline__ void imma_u8(int (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
     asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
