@@ -30,8 +30,6 @@ constexpr int PW_PEN = 1 << 29;  // an excluded element's accumulator (-S) start
 __device__ __forceinline__ int pw_gate(int m) { return m > 0x7fffffff - ((OSD_WIN + 1) << 7) ? 0x7fffffff : ((((m >> 7) + OSD_WIN) << 7) | 127); }
 // the tiles hold -S: packed score <= gate  <=>  S <= gate >> 7  <=>  -S >= -(gate >> 7)   (the low seven bits of a gate are ones)
 __device__ __forceinline__ int pw_gate_neg(int gate) { return -(gate >> 7); }
-// four bits -> four bytes of 0/2 (bit k of the nibble in byte k): B operand of the low weight plane, x 64 = of the high one
-__device__ __forceinline__ unsigned spread4x2(unsigned word, int sh) { return (((word >> sh) & 0xFu) * 0x00408102u) & 0x02020202u; }
 
 __global__ void __launch_bounds__(OSD_THREADS, 6) osd_pair_kernel(OsdArgs a, const uint64_t* __restrict__ gcol) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -93,6 +93,8 @@ __device__ __forceinline__ void imma_u8(int (&c)[4], const unsigned (&a)[4], con
 }
 // four bits -> four bytes of 0/1 (bit k of the nibble in byte k)
 __device__ __forceinline__ unsigned spread4(unsigned word, int sh) { return (((word >> sh) & 0xFu) * 0x00204081u) & 0x01010101u; }
+// four bits -> four bytes of 0/2 (bit k of the nibble in byte k): B operand of the low weight plane, << 6 = of the high one
+__device__ __forceinline__ unsigned spread4x2(unsigned word, int sh) { return (((word >> sh) & 0xFu) * 0x00408102u) & 0x02020202u; }
 // four bits -> four bytes of 0x00/0xFF: the bits are moved to the byte sign positions and replicated by PRMT
 __device__ __forceinline__ unsigned mask4(unsigned word, int sh) {
     const unsigned x = ((word >> sh) & 0xFu) * 0x10204080u;
