@@ -39,7 +39,7 @@ struct __align__(16) Osd3Warp {
 
 constexpr int O3_NONE = 64;  // pass without a third position
 constexpr int O3_INF = 0x7fffffff;
-constexpr int O3_PEN = 1 << 20;   // x 512 = 2^29 added to the score of an element outside the triangle i < j < kl
+constexpr int O3_PEN = 1 << 29;   // an element outside the triangle i < j < kl starts its accumulator (-S) this much lower
 constexpr int O3_BIG = 1 << 29;
 // candidate ids: pass << 8 | mi << 6 | nj << 3 | e << 1 ... kept simple: fields below
 __device__ __forceinline__ int o3_id(int pass, int mi, int nj, int e) { return (pass << 7) | (mi << 5) | (nj << 2) | e; }
@@ -92,8 +92,8 @@ __global__ void __launch_bounds__(OSD_THREADS, FS ? 3 : 4) osd3_kernel(OsdArgs a
         build_shfl_tables(F, lane, tb);
         {
             const unsigned wa = F.w32[lane], wb = F.w32[lane + 32];
-            W.C[lane] = F.qd32[lane] + wpop_shfl(tb, P.myprow[0]);
-            W.C[lane + 32] = F.qd32[lane + 32] + wpop_shfl(tb, P.myprow[1]);
+            W.C[lane] = -(F.qd32[lane] + wpop_shfl(tb, P.myprow[0]));  // -C_j: the low-plane accumulators start at -(R_i + C_j)
+            W.C[lane + 32] = -(F.qd32[lane + 32] + wpop_shfl(tb, P.myprow[1]));
             if (FS) { W.HC[lane] = __popcll(P.myprow[0]); W.HC[lane + 32] = __popcll(P.myprow[1]); }
             __syncwarp();  // every lane is done with w32 as words: the byte planes go to ys
             unsigned char* wq = reinterpret_cast<unsigned char*>(F.ys);  // [plane][LRB position]
@@ -104,8 +104,8 @@ __global__ void __launch_bounds__(OSD_THREADS, FS ? 3 : 4) osd3_kernel(OsdArgs a
         for (int x = 0; x < 8; ++x) {
             // B fragments: column j = 8x + g, this thread's nibbles of P'_j
             const unsigned long long cj = F.prow[8 * x + g];
-            W.bfrag[x][lane] = make_uint4(spread4((unsigned)cj, 4 * t), spread4((unsigned)cj, 4 * t + 16),
-                                          spread4((unsigned)(cj >> 32), 4 * t), spread4((unsigned)(cj >> 32), 4 * t + 16));
+            W.bfrag[x][lane] = make_uint4(spread4x2((unsigned)cj, 4 * t), spread4x2((unsigned)cj, 4 * t + 16),
+                                          spread4x2((unsigned)(cj >> 32), 4 * t), spread4x2((unsigned)(cj >> 32), 4 * t + 16));
             // masks of rows 8x + g (the same nibbles)
             W.maskp[8 * x + g][t] = make_uint4(mask4((unsigned)cj, 4 * t), mask4((unsigned)cj, 4 * t + 16),
                                               mask4((unsigned)(cj >> 32), 4 * t), mask4((unsigned)(cj >> 32), 4 * t + 16));
@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(OSD_THREADS, FS ? 3 : 4) osd3_kernel(OsdArgs a
 
         int s[3] = {O3_INF, O3_INF, O3_INF}, sid[3] = {0, 0, 0};
         int gate = O3_INF;  // running warp minimum + OSD_WIN
+        int gn = -O3_INF;   // -gate: the tiles hold -S
         const int b32 = F.base32;
         // ---- passes: no third position (pairs, singles, the empty TEP), then k = 2..63 ------------------------
         bool any_stop = false;
@@ -130,17 +131,17 @@ __global__ void __launch_bounds__(OSD_THREADS, FS ? 3 : 4) osd3_kernel(OsdArgs a
             const int bk = b32 + (pass == O3_NONE ? 0 : F.qd32[pass]);
             __syncwarp();  // the previous pass is done with R
             if (pass != O3_NONE && lane == 0) {  // j < kl: passes run downwards, every j > kl is already out
-                W.C[pass] = O3_BIG;
+                W.C[pass] = -O3_BIG;
                 if (FS) W.HC[pass] = O3_PEN;
             }
             {
                 const int r0 = bk + F.qd32[lane] + wpop_shfl(tb, dk ^ P.myprow[0]);
-                W.R[lane] = r0;
+                W.R[lane] = -r0;
                 if (FS) { W.HR[lane] = __popcll(dk ^ P.myprow[0]); W.HR[lane + 32] = __popcll(dk ^ P.myprow[1]); }
                 int r1 = O3_INF;
                 if (kl > 32) {  // warp-uniform
                     r1 = bk + F.qd32[lane + 32] + wpop_shfl(tb, dk ^ P.myprow[1]);
-                    W.R[lane + 32] = r1;
+                    W.R[lane + 32] = -r1;
                 }
                 if (pass == O3_NONE) {  // warp-uniform
                     o3_track(s, sid, r0, O3_ID_SINGLE | lane);
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(OSD_THREADS, FS ? 3 : 4) osd3_kernel(OsdArgs a
                     const int ez = bk + wpop_shfl(tb, dk);  // the empty TEP (shuffles are warp-wide: every lane computes it)
                     if (lane == 0) o3_track(s, sid, ez, O3_ID_EMPTY);
                     gate = __reduce_min_sync(0xffffffffu, s[0]) + OSD_WIN;
+                    gn = -gate;
                 }
             }
             const uint4 md = make_uint4(mask4((unsigned)dk, 4 * t), mask4((unsigned)dk, 4 * t + 16),
@@ -183,34 +185,33 @@ __global__ void __launch_bounds__(OSD_THREADS, FS ? 3 : 4) osd3_kernel(OsdArgs a
                 }
                 const int hr0 = FS ? W.HR[i0] : 0, hr1 = FS ? W.HR[i0 + 8] : 0;
                 const int rr0 = W.R[i0], rr1 = W.R[i0 + 8];
-                // One 16x8 tile: four IMMAs, scores, gate.  `pen` initialises the high-plane accumulators: -O3_PEN on the
-                // elements with i >= j of the two tiles that touch the diagonal (their score comes out 2^29 too large and
-                // never passes the gate), 0 elsewhere -- the triangle costs no instruction.  Columns j >= kl carry the
-                // same penalty in C (set once per pass, see above).
-                // scores of one tile (p4) from its four (FS: six) IMMAs
+                // One 16x8 tile.  The B bytes are 0/2, so the two planes accumulate 2 M_lo and 2 M_hi; the low-plane
+                // accumulator starts at -(R_i + C_j) -- `pen` lower on the elements with i >= j of the two tiles that touch
+                // the diagonal, and columns j >= kl carry the same penalty in C, so the triangle costs no instruction -- and
+                // one multiply-add per element, acc0 + 256 acc1, gives -S(i,j).
                 auto tile_scores = [&](int nj, const int (&pen)[4], int (&p4)[4]) {
                     const uint4 bf = W.bfrag[nj][lane];
                     const unsigned b0[2] = {bf.x, bf.y}, b1[2] = {bf.z, bf.w};
-                    int acc0[4] = {0, 0, 0, 0}, acc1[4] = {pen[0], pen[1], pen[2], pen[3]};
+                    const int2 cc = *reinterpret_cast<const int2*>(W.C + 8 * nj + 2 * t);
+                    int acc0[4] = {rr0 + cc.x + pen[0], rr0 + cc.y + pen[1], rr1 + cc.x + pen[2], rr1 + cc.y + pen[3]};
+                    int acc1[4] = {0, 0, 0, 0};
                     imma_u8(acc0, afr[0][0], b0);
                     imma_u8(acc1, afr[0][1], b0);
                     imma_u8(acc0, afr[1][0], b1);
                     imma_u8(acc1, afr[1][1], b1);
-                    const int2 cc = *reinterpret_cast<const int2*>(W.C + 8 * nj + 2 * t);
-                    const int rc[4] = {rr0 + cc.x, rr0 + cc.y, rr1 + cc.x, rr1 + cc.y};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) p4[e] = rc[e] - 2 * acc0[e] - 512 * acc1[e];
+                    for (int e = 0; e < 4; ++e) p4[e] = acc0[e] + 256 * acc1[e];
                     if (FS) {
-                        int acch[4] = {pen[0], pen[1], pen[2], pen[3]};  // excluded elements come out 2^21 too far
-                        imma_u8(acch, afh[0], b0);
+                        int acch[4] = {pen[0], pen[1], pen[2], pen[3]};  // excluded elements come out 2^29 too far
+                        imma_u8(acch, afh[0], b0);  // B bytes are 2: acch = 2 sum u.P_j
                         imma_u8(acch, afh[1], b1);
                         const int2 hc = *reinterpret_cast<const int2*>(W.HC + 8 * nj + 2 * t);
                         const int hrc[4] = {hr0 + hc.x, hr0 + hc.y, hr1 + hc.x, hr1 + hc.y};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const int hd = hrc[e] - 2 * acch[e];
+                            const int hd = hrc[e] - acch[e];
                             any_stop |= hd < fs.hs;
-                            if (hd >= fs.he) p4[e] = O3_INF;
+                            if (hd >= fs.he) p4[e] = -O3_INF;
                         }
                     }
                 };
@@ -218,20 +219,18 @@ __global__ void __launch_bounds__(OSD_THREADS, FS ? 3 : 4) osd3_kernel(OsdArgs a
                 auto offer = [&](int nj, const int (&p4)[4]) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
-                        if (p4[e] <= gate) o3_track(s, sid, p4[e], o3_id(pass, mi, nj, e));
+                        if (p4[e] >= gn) o3_track(s, sid, -p4[e], o3_id(pass, mi, nj, e));
                 };
                 auto regate = [&]() {
                     const int wm = __reduce_min_sync(0xffffffffu, s[0]);
                     gate = wm > O3_INF - OSD_WIN ? O3_INF : wm + OSD_WIN;
+                    gn = -gate;
                 };
-                // One 16x8 tile.  `pen` initialises the high-plane accumulators: -O3_PEN on the elements with i >= j of
-                // the two tiles that touch the diagonal (their score comes out 2^29 too large and never passes the gate),
-                // 0 elsewhere -- the triangle costs no instruction.  Columns j >= kl carry the same penalty in C.
                 auto tile = [&](int nj, const int (&pen)[4]) {
                     int p4[4];
                     tile_scores(nj, pen, p4);
-                    const int m4 = min(min(p4[0], p4[1]), min(p4[2], p4[3]));
-                    if (__any_sync(0xffffffffu, m4 <= gate)) {
+                    const int m4 = max(max(p4[0], p4[1]), max(p4[2], p4[3]));
+                    if (__any_sync(0xffffffffu, m4 >= gn)) {
                         offer(nj, p4);
                         regate();
                     }
@@ -241,8 +240,8 @@ __global__ void __launch_bounds__(OSD_THREADS, FS ? 3 : 4) osd3_kernel(OsdArgs a
                     int pa[4], pb[4];
                     tile_scores(nj, pen_none, pa);
                     tile_scores(nj + 1, pen_none, pb);
-                    const int m8 = min(min(min(pa[0], pa[1]), min(pa[2], pa[3])), min(min(pb[0], pb[1]), min(pb[2], pb[3])));
-                    if (__any_sync(0xffffffffu, m8 <= gate)) {
+                    const int m8 = max(max(max(pa[0], pa[1]), max(pa[2], pa[3])), max(max(pb[0], pb[1]), max(pb[2], pb[3])));
+                    if (__any_sync(0xffffffffu, m8 >= gn)) {
                         offer(nj, pa);
                         offer(nj + 1, pb);
                         regate();
