@@ -119,7 +119,7 @@ def test_pair_sweep_equals_lut_sweep_on_a_million_frames(handle, tep_order, ebn0
     assert torch.equal(bt, ba[:, 0])
 
 
-@pytest.mark.parametrize("threshold_sum,quantised", [(2, False), (3, False), (3, True)])
+@pytest.mark.parametrize("threshold_sum,quantised", [(2, False), (2, True), (3, False), (3, True)])
 def test_block_minima_truncated_sweep_equals_lut_sweep_on_many_frames(code, threshold_sum, quantised):
     """osd_blocks.cu (per-block truncated shuffle-table sweep + exact re-scoring of the window, marked blocks redone
     through the byte LUT) against the byte-LUT sweep of round 1 (LDPCB_BLOCKS_LUT=1) on the NMS failures of 2^19 frames:
