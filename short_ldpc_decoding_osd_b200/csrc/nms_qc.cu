@@ -193,9 +193,10 @@ __global__ void __launch_bounds__(QC_THREADS, MINB) nms_qc_kernel(NmsArgs a, Nms
 #pragma unroll
             for (int e = 0; e < 8; ++e) cv[R][e] = 0.0f;
 
-        // two iterations per trip save the register moves of the loop-carried messages in the plain kernels (5.60 -> 5.49 ms per
-        // 2^21 frames); the fused kernel (117 registers when unrolled) is faster as it is
-#pragma unroll(FUSE ? 1 : 2)
+        // two iterations per trip save the register moves of the loop-carried messages: plain kernel 5.60 -> 5.48 ms per 2^21
+        // frames, generator-fused kernel 4.58 -> 4.52 ms per 2^20 (with OSD); the fused decode kernel alone is slower unrolled
+        // (5.56 -> 5.63 ms, measured twice) and keeps one iteration per trip
+#pragma unroll((FUSE && !GEN) ? 1 : 2)
         for (int it = 0; it < a.iters; ++it) {
             // ---- check phase: vc = total - cv_old (ms_test.py:133-136), min1/min2/sign (:184-206), new cv (:207-209) ----
             static_for<4>([&](auto Rc) {

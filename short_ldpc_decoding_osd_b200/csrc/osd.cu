@@ -15,9 +15,11 @@
 //      bits); a frame in which two keys agree in their upper 24 bits is re-sorted with (key, index) pairs, and
 //      one with two equal keys (2.7e-4 of AWGN frames, every frame of a quantised input) is re-ranked by an
 //      exact rank sort with tf.argsort's tie rule.
-//   2. column-major GF(2) elimination of G[:, pi1]: lane l holds sorted columns 4l..4l+3 as 64-bit
-//      words (bit r = row r); columns are scanned most reliable first, a column with a 1 in a row not
-//      yet used becomes the next pivot (greedy most-reliable basis).  The reference's rule (row swap /
+//   2. column-major GF(2) elimination of G[:, pi1]: lane l holds sorted columns l, l+32, l+64, l+96 as 64-bit
+//      words (bit r = row r); columns are taken most reliable first, a column with a 1 in a row not
+//      yet used becomes the next pivot (greedy most-reliable basis).  Unit columns of G among the 64 most
+//      reliable positions join the basis on their own row without a visit; only the other columns are visited
+//      (osd_prepare.cuh step 2 says how the pivot rows are chosen so that this is exact).  The reference's rule (row swap /
 //      column swap with the first 1 of row i) selects the same basis and its outputs depend only on
 //      that basis because identify_mrb re-sorts both halves (pb_testing.py:284-300); DESIGN.md gives
 //      the argument, tests compare with the reference's own full_gf2elim.
@@ -27,7 +29,8 @@
 // score = base + sum delta_t + W(D), W the weighted popcount over the 64 LRB reliabilities.
 //   5a. orders 0, 1, 3: truncated 32-bit scores through thirteen 5-bit tables held one entry per lane (shuffles)
 //   5b. order 2: the tensor-core pair sweep below (IMMA over masked weight byte planes)
-//   5c. block minima (DL path), FS policy and the near-tie fallback: exact 64-bit scores through byte LUTs
+//   5c. block minima (DL path): osd_blocks.cu (truncated scores per block + exact re-scoring); FS policy and the
+//       near-tie fallbacks: exact 64-bit scores through byte LUTs
 //   6. the TEPs within the truncation window of the minimum are re-scored exactly; lexicographic
 //      (score, index) minimum = first minimum in enumeration order (tf.argmin)
 #include <cmath>
