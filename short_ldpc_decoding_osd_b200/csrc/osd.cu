@@ -45,7 +45,7 @@ namespace ldpcb {
 // SOLO (full order-0/1 lists): every warp sweeps its own frame -- 65 TEPs are three per lane -- so the CTA needs no
 // barrier, no LUT and no table in shared memory (the dynamic shared memory then holds the four FrameSm only).
 template <int MAXW, bool BLOCKS, bool SOLO>
-__global__ void __launch_bounds__(OSD_THREADS, 6) osd_kernel(OsdArgs a, const uint64_t* __restrict__ gcol) {
+__global__ void __launch_bounds__(OSD_THREADS, SOLO ? 8 : 6) osd_kernel(OsdArgs a, const uint64_t* __restrict__ gcol) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     OsdSmem& S = *reinterpret_cast<OsdSmem*>(smem_raw);  // not touched when SOLO
     const int tid = threadIdx.x;

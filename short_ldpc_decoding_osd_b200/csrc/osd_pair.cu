@@ -31,7 +31,7 @@ __device__ __forceinline__ int pw_gate(int m) { return m > 0x7fffffff - ((OSD_WI
 // the tiles hold -S: packed score <= gate  <=>  S <= gate >> 7  <=>  -S >= -(gate >> 7)   (the low seven bits of a gate are ones)
 __device__ __forceinline__ int pw_gate_neg(int gate) { return -(gate >> 7); }
 
-__global__ void __launch_bounds__(OSD_THREADS, 6) osd_pair_kernel(OsdArgs a, const uint64_t* __restrict__ gcol) {
+__global__ void __launch_bounds__(OSD_THREADS, 7) osd_pair_kernel(OsdArgs a, const uint64_t* __restrict__ gcol) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PairSmem& S = *reinterpret_cast<PairSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
