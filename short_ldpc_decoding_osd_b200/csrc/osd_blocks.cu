@@ -18,16 +18,18 @@
 namespace ldpcb {
 
 struct __align__(16) BlocksSmem {
-    unsigned long long lut[8][256];  // exact redo only
+    union {
+        unsigned long long lut[8][256];  // exact redo only (after barrier (A): the sweeps are over)
+        uint4 comb[OSD_FPB][K + 1];      // sweep: {P' row, floor(qd / 2^30)} of MRB position t in one 16-byte load, [64] = 0
+    };
     FrameSm fr[OSD_FPB];
-    uint4 comb[OSD_FPB][K + 1];      // {P' row, floor(qd / 2^30)} of MRB position t in one 16-byte load, [64] = 0
     int fb[OSD_FPB];                 // frame of warp w has marked blocks
 };
 
 constexpr long long BLK_MARK = -1;  // exact scores are >= 0
 
 template <int MAXW>
-__global__ void __launch_bounds__(OSD_THREADS, 6) osd_blocks_kernel(OsdArgs a, const uint64_t* __restrict__ gcol) {
+__global__ void __launch_bounds__(OSD_THREADS, 7) osd_blocks_kernel(OsdArgs a, const uint64_t* __restrict__ gcol) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BlocksSmem& S = *reinterpret_cast<BlocksSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
