@@ -34,6 +34,7 @@
 //   6. the TEPs within the truncation window of the minimum are re-scored exactly; lexicographic
 //      (score, index) minimum = first minimum in enumeration order (tf.argmin)
 #include <cmath>
+#include <cstddef>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -496,7 +497,7 @@ __global__ void __launch_bounds__(OSD_THREADS) osd_fs_kernel(OsdArgs a, FsParams
 
 int launch_osd_fs(ldpcb_handle* h, const OsdArgs& a, const FsParams& fp, cudaStream_t st) {
     if (a.B == 0) return LDPCB_OK;
-    const int smem = (int)sizeof(OsdSmem);
+    const int smem = (int)offsetof(OsdSmem, tabs);  // the FS sweeps score through the byte LUT: the shuffle-table copies (last member, 6.5 KB) are not touched -> 7 instead of 5 CTAs per SM
     int& occ = h->occ[OCC_OSD_FS];
     if (occ == 0) {
         LDPCB_CUDA(h, cudaFuncSetAttribute(osd_fs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
