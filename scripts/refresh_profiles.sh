@@ -3,7 +3,7 @@
 # text / JSON files under profiles/.
 set -e
 cd "$(dirname "$0")/.."
-python scripts/make_traffic.py gpurun_out/prof_final.ncu-rep gpurun_out/prof_stamp.json > /dev/null
+cp gpurun_out/f_traffic.json profiles/r02_traffic.json  # made on the GPU box right after the capture (scripts/final_captures.sh)
 python scripts/ncu_kernel_report.py gpurun_out/prof_final.ncu-rep nms_qc 131072 > profiles/r02_ncu_nms_qc.txt
 python scripts/ncu_kernel_report.py gpurun_out/prof_final.ncu-rep osd_pair 131072 > profiles/r02_ncu_osd_pair.txt
 python scripts/ncu_kernel_report.py gpurun_out/prof_final.ncu-rep osd_kernel 131072 > profiles/r02_ncu_osd_order1.txt
